@@ -1,0 +1,121 @@
+"""ctypes binding of the apb C ABI (include/apb.h).
+
+The product library is ark_plonk_b200/lib/libapb.so (built by ark_plonk_b200/build.py with
+nvcc for sm_100a).  There is no CPU fallback: if the library is missing or no CUDA device is
+present, calls raise.  (`Lib(path)` also lets the CPU test-suite bind the emulation build of
+the same kernel sources; the package itself never does.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "lib", "libapb.so")
+
+CURVE_BLS12_381 = 0
+CURVE_BLS12_377 = 1
+NTT_FFT, NTT_IFFT, NTT_COSET_FFT, NTT_COSET_IFFT = 0, 1, 2, 3
+
+STATUS_NAMES = {
+    1: "InvalidArgument", 2: "TooManyCoefficients", 3: "InvalidEvalDomainSize",
+    4: "BadHandle", 5: "CudaError", 6: "OutOfMemory",
+}
+
+
+class ApbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(code, "status %d" % code), msg))
+        self.code = code
+
+
+class Lib:
+    def __init__(self, path: str = DEFAULT_LIB):
+        if not os.path.exists(path):
+            raise ApbError(5, "native library %s not found - run `python -m ark_plonk_b200.build` "
+                              "(there is no CPU fallback)" % path)
+        self.path = path
+        self.c = C.CDLL(path)
+        c = self.c
+        vp, sz, u64p, ci = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_int
+        c.apb_init.argtypes = [ci]
+        c.apb_last_error.restype = C.c_char_p
+        c.apb_version.restype = C.c_char_p
+        c.apb_ck_upload.argtypes = [ci, vp, sz, C.POINTER(vp)]
+        c.apb_ck_size.argtypes = [vp, C.POINTER(sz)]
+        c.apb_ck_free.argtypes = [vp]
+        c.apb_ck_free.restype = None
+        c.apb_msm.argtypes = [vp, sz, vp, sz, ci, vp]
+        c.apb_msm_batch.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), ci, vp]
+        c.apb_msm_dev.argtypes = [vp, sz, vp, sz, ci, vp]
+        c.apb_msm_batch_dev.argtypes = [vp, sz, vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), ci, vp]
+        c.apb_g1_compress.argtypes = [ci, vp, vp]
+        c.apb_domain_new.argtypes = [ci, C.c_uint32, C.POINTER(vp)]
+        c.apb_domain_size.argtypes = [vp, C.POINTER(sz)]
+        c.apb_domain_free.argtypes = [vp]
+        c.apb_domain_free.restype = None
+        c.apb_ntt.argtypes = [vp, ci, vp, sz, vp]
+        c.apb_ntt_dev.argtypes = [vp, ci, vp, sz, vp, ci]
+        c.apb_ntt_batch_dev.argtypes = [vp, ci, vp, sz, sz, vp, sz, sz, ci]
+        c.apb_dev_alloc.argtypes = [sz, C.POINTER(vp)]
+        c.apb_dev_free.argtypes = [vp]
+        c.apb_dev_upload.argtypes = [vp, vp, sz]
+        c.apb_dev_download.argtypes = [vp, vp, sz]
+        c.apb_stream.restype = vp
+        c.apb_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
+        c.apb_kernel_launches.restype = C.c_uint64
+        c.apb_imad_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        c.apb_last_device_ms.restype = C.c_double
+
+    # ------------------------------------------------------------------
+    def check(self, rc: int):
+        if rc != 0:
+            raise ApbError(rc, self.c.apb_last_error().decode())
+
+    def init(self, device: int = -1):
+        self.check(self.c.apb_init(device))
+
+    def version(self) -> str:
+        return self.c.apb_version().decode()
+
+    def kernel_launches(self) -> int:
+        return int(self.c.apb_kernel_launches())
+
+    def last_device_ms(self) -> float:
+        return float(self.c.apb_last_device_ms())
+
+    def imad_peak(self):
+        w, n = C.c_double(), C.c_double()
+        self.check(self.c.apb_imad_peak(C.byref(w), C.byref(n)))
+        return w.value, n.value
+
+    @staticmethod
+    def _ptr(a: np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def field_op(self, field: int, op: int, a: np.ndarray, b: np.ndarray | None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        bb = np.ascontiguousarray(b, dtype=np.uint64) if b is not None else None
+        self.check(self.c.apb_field_op(field, op, self._ptr(a), self._ptr(bb) if bb is not None else None,
+                                       self._ptr(out), a.shape[0]))
+        return out
+
+    def g1_compress(self, curve: int, xyz: np.ndarray) -> bytes:
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint64)
+        out = np.empty(48, dtype=np.uint8)
+        self.check(self.c.apb_g1_compress(curve, self._ptr(xyz), self._ptr(out)))
+        return out.tobytes()
+
+
+_LIB: Lib | None = None
+
+
+def get_lib() -> Lib:
+    """The product library (CUDA).  Raises if it is not built or no GPU is present."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib(DEFAULT_LIB)
+    return _LIB

@@ -1,0 +1,206 @@
+// Library state, initialisation, device-memory helpers and diagnostics of the apb C ABI.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace apb {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+cudaStream_t g_stream = nullptr;
+bool g_inited = false;
+double g_last_ms = 0.0;
+extern int g_num_sms;
+
+int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+template <class P>
+__global__ void k_field_op(int op, const void* a, const void* b, void* out, uint64_t count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fp<P> x = load_fp<P>(a, i), r;
+    if (op <= 2) {
+        Fp<P> y = load_fp<P>(b, i);
+        r = op == 0 ? x * y : (op == 1 ? x + y : x - y);
+    } else {
+        r = op == 3 ? x.to_mont() : x.from_mont();
+    }
+    store_fp<P>(out, i, r);
+}
+
+// Throughput microbenchmark: ILP independent carry-free multiply-add chains per thread.
+// WIDE = 1: mad.wide.u32 (64-bit accumulate, the IMAD.WIDE the Montgomery chains compile to);
+// WIDE = 0: mad.lo.u32.
+template <int WIDE>
+__global__ void __launch_bounds__(256) k_imad_bench(uint32_t* out, uint32_t iters, uint32_t seed) {
+#ifdef __CUDA_ARCH__
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    if (WIDE) {
+        unsigned long long acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = a + k;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            }
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= acc[k];
+        if (s == 0x1234567) out[0] = (uint32_t)s;
+    } else {
+        uint32_t acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = a + k;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b));
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= acc[k];
+        if (s == 0x1234567) out[0] = s;
+    }
+#else
+    (void)out; (void)iters; (void)seed;
+#endif
+}
+
+}  // namespace apb
+
+using namespace apb;
+
+extern "C" int apb_init(int device) {
+    if (g_inited) return APB_OK;
+#ifndef APB_EMU
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(APB_ERR_CUDA, "apb_init: no CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device >= 0) APB_CUDA_TRY(cudaSetDevice(device));
+    int dev = 0;
+    APB_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    APB_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    g_num_sms = prop.multiProcessorCount;
+#else
+    (void)device;
+    g_num_sms = 1;
+#endif
+    APB_CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_inited = true;
+    return APB_OK;
+}
+
+extern "C" const char* apb_last_error(void) { return g_err; }
+extern "C" const char* apb_version(void) {
+#ifdef APB_EMU
+    return "apb 0.1 (CPU emulation build - tests only)";
+#else
+    return "apb 0.1 (sm_100a)";
+#endif
+}
+extern "C" uint64_t apb_kernel_launches(void) { return g_launches.load(); }
+extern "C" double apb_last_device_ms(void) { return g_last_ms; }
+extern "C" void* apb_stream(void) { return (void*)g_stream; }
+
+extern "C" int apb_dev_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr) return set_err(APB_ERR_INVALID_ARG, "apb_dev_alloc: null out");
+    APB_REQUIRE_INIT();
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return set_err(APB_ERR_OOM, "apb_dev_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return APB_OK;
+}
+extern "C" int apb_dev_free(void* d_ptr) {
+    if (d_ptr) APB_CUDA_TRY(cudaFree(d_ptr));
+    return APB_OK;
+}
+extern "C" int apb_dev_upload(void* d_dst, const void* h_src, size_t bytes) {
+    APB_REQUIRE_INIT();
+    APB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+extern "C" int apb_dev_download(void* h_dst, const void* d_src, size_t bytes) {
+    APB_REQUIRE_INIT();
+    APB_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+extern "C" int apb_dev_sync(void) {
+    APB_REQUIRE_INIT();
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+
+extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count) {
+    if (field < 0 || field > 3 || op < 0 || op > 4) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: bad field/op");
+    if (!a || !out || (op <= 2 && !b)) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: null argument");
+    if (count == 0) return APB_OK;
+    APB_REQUIRE_INIT();
+    const size_t esz = (field == 0 || field == 2) ? 32 : 48;
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    APB_CUDA_TRY(cudaMalloc(&da, count * esz));
+    APB_CUDA_TRY(cudaMalloc(&db, count * esz));
+    APB_CUDA_TRY(cudaMalloc(&dout, count * esz));
+    APB_CUDA_TRY(cudaMemcpyAsync(da, a, count * esz, cudaMemcpyHostToDevice, g_stream));
+    if (b) APB_CUDA_TRY(cudaMemcpyAsync(db, b, count * esz, cudaMemcpyHostToDevice, g_stream));
+    unsigned blocks = (unsigned)((count + 127) / 128);
+    switch (field) {
+        case 0: APB_KLAUNCH(k_field_op<Fr381>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
+        case 1: APB_KLAUNCH(k_field_op<Fq381>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
+        case 2: APB_KLAUNCH(k_field_op<Fr377>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
+        default: APB_KLAUNCH(k_field_op<Fq377>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
+    }
+    APB_CHECK_LAUNCH();
+    APB_CUDA_TRY(cudaMemcpyAsync(out, dout, count * esz, cudaMemcpyDeviceToHost, g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return APB_OK;
+}
+
+extern "C" int apb_imad_peak(double* wide_per_s, double* imad32_per_s) {
+    APB_REQUIRE_INIT();
+    uint32_t* d_out = nullptr;
+    APB_CUDA_TRY(cudaMalloc((void**)&d_out, 64));
+    const uint32_t iters = 4096;
+    const unsigned blocks = (unsigned)g_num_sms * 8, threads = 256;
+    double res[2] = {0, 0};
+    for (int wide = 0; wide < 2; wide++) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0, g_stream);
+            if (wide) APB_KLAUNCH(k_imad_bench<1>, blocks, threads, 0, d_out, iters, 12345u + rep);
+            else APB_KLAUNCH(k_imad_bench<0>, blocks, threads, 0, d_out, iters, 12345u + rep);
+            cudaEventRecord(e1, g_stream);
+            APB_CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        double ops = (double)blocks * threads * iters * 32.0;
+        res[wide] = best > 0 ? ops / (best * 1e-3) : 0;
+    }
+    cudaFree(d_out);
+    if (wide_per_s) *wide_per_s = res[1];
+    if (imad32_per_s) *imad32_per_s = res[0];
+    return APB_OK;
+}

@@ -1,0 +1,723 @@
+// Variable-base multi-scalar multiplication over G1 (BLS12-381 / BLS12-377) for sm_100a.
+//
+// Replaces ark_ec::msm::VariableBaseMSM::multi_scalar_mul (plonk-core/src/commitment.rs:45 and,
+// through SonicKZG10::commit/open, plonk-core/src/proof_system/prover.rs:213,290,313,316,362,388,
+// 459,579,582,606,609; preprocess.rs:351; lookup/preprocess.rs:63).  Same function
+// (sum_i s_i * P_i), different algorithm; the result is unique as a group element and leaves
+// the library as a normalised affine point.
+//
+// Design (B200-first, see DESIGN.md "MSM"):
+//   * The commitment key is resident in HBM together with F-1 precomputed multiples
+//     2^(step*f) * P_i (affine).  A signed c-bit digit at position w = f*G + g of scalar i is
+//     then "add +-copy_f[i] to bucket |d|-1 of effective window g": with step = 16, c = 16,
+//     G = 1 all 16 digit positions share ONE bucket set and no window doublings remain.
+//   * digits -> histogram -> exclusive scan -> scatter gives the (bucket, point) pairs sorted
+//     by bucket (a counting sort; keys are bucket ids).
+//   * accumulation walks the sorted list in equal chunks per thread (perfect balance for any
+//     scalar distribution); runs that cross chunk borders are stitched by a second kernel.
+//   * the weighted bucket sum  sum_b (b+1) * S_b  is evaluated with log-depth trees only:
+//     buckets are viewed as a 2^a x 2^b matrix, row/column sums are trees, and the two small
+//     weighted sums are split by weight bit (V_k = sum of entries whose weight has bit k set).
+//   * the last ~40 group operations (Horner over the V_k, window fold, one inversion) run on
+//     the host in 64-bit limbs: they are a strictly sequential chain and the result is needed
+//     in host memory for the transcript.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "host_ec.hpp"
+
+namespace apb {
+
+int g_num_sms = 1;
+
+static const int MAX_BATCH = 16;
+#ifdef APB_EMU
+static const int SCAN_THREADS = 64;
+#else
+static const int SCAN_THREADS = 1024;
+#endif
+static const int MAX_COPIES = 16;
+
+struct MsmBatch {
+    uint32_t k;
+    uint64_t scal_off[MAX_BATCH];    // element offset into the concatenated scalar buffer
+    uint64_t base_off[MAX_BATCH];
+    uint64_t len[MAX_BATCH];
+};
+
+struct MsmGeom {
+    uint32_t c;          // digit bits
+    uint32_t G;          // effective windows (bucket groups)
+    uint32_t W;          // digit positions
+    uint32_t hb;         // buckets per window = 2^(c-1)
+    uint64_t ck_n;       // points per copy in the resident table
+};
+
+// ---- scalar recoding ---------------------------------------------------------------------
+template <class FR>
+APB_D bool geq_mod(const Fp<FR>& a) {
+#pragma unroll
+    for (int i = FR::N - 1; i >= 0; i--) {
+        if (a.v[i] > FR::mod(i)) return true;
+        if (a.v[i] < FR::mod(i)) return false;
+    }
+    return true;
+}
+template <class FR>
+APB_D bool gt_half(const Fp<FR>& a) {
+#pragma unroll
+    for (int i = FR::N - 1; i >= 0; i--) {
+        if (a.v[i] > FR::half_mod(i)) return true;
+        if (a.v[i] < FR::half_mod(i)) return false;
+    }
+    return false;
+}
+template <class FR>
+APB_D void sub_mod_raw(Fp<FR>& a) {
+    a.v[0] = sub_cc(a.v[0], FR::mod(0));
+#pragma unroll
+    for (int i = 1; i < FR::N - 1; i++) a.v[i] = subc_cc(a.v[i], FR::mod(i));
+    a.v[FR::N - 1] = subc(a.v[FR::N - 1], FR::mod(FR::N - 1));
+}
+
+// canonical |s| <= (r-1)/2 and the sign that was factored out
+template <class FR>
+APB_D Fp<FR> load_scalar(const void* scalars, uint64_t idx, int mont, bool& negative) {
+    Fp<FR> s = load_fp<FR>(scalars, idx);
+    if (mont) s = s.from_mont();
+    else while (geq_mod<FR>(s)) sub_mod_raw<FR>(s);
+    negative = gt_half<FR>(s);
+    if (negative) s = s.neg();            // r - s
+    return s;
+}
+
+// digit at position w (c bits from bit w*c) plus incoming carry; returns signed digit, updates carry
+template <class FR>
+APB_D int take_digit(const Fp<FR>& s, uint32_t w, uint32_t c, uint32_t& carry) {
+    uint32_t lo = w * c;
+    uint32_t limb = lo >> 5, sh = lo & 31;
+    uint64_t window = limb < (uint32_t)FR::N ? s.v[limb] : 0;
+    if (limb + 1 < (uint32_t)FR::N) window |= (uint64_t)s.v[limb + 1] << 32;
+    uint32_t raw = (uint32_t)((window >> sh) & ((1u << c) - 1)) + carry;
+    if (raw > (1u << (c - 1))) {
+        carry = 1;
+        return (int)raw - (int)(1u << c);
+    }
+    carry = 0;
+    return (int)raw;
+}
+
+// pass 0: histogram; pass 1: scatter (digits are recomputed instead of stored)
+template <class FR, int PASS>
+__global__ void k_msm_digits(const void* scalars, MsmBatch B, MsmGeom g, int mont, uint32_t* counts,
+                             const uint32_t* offsets, uint32_t* cursors, uint32_t* entries) {
+    const uint32_t j = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.len[j]) return;
+    bool negative;
+    Fp<FR> s = load_scalar<FR>(scalars, B.scal_off[j] + i, mont, negative);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < g.W; w++) {
+        int d = take_digit<FR>(s, w, g.c, carry);
+        if (d == 0) continue;
+        bool neg = negative != (d < 0);
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t f = w / g.G, gw = w % g.G;
+        uint32_t bucket = (j * g.G + gw) * g.hb + (mag - 1);
+        if (PASS == 0) {
+            atomicAdd(&counts[bucket], 1u);
+        } else {
+            uint32_t pos = offsets[bucket] + atomicAdd(&cursors[bucket], 1u);
+            uint64_t pidx = (uint64_t)f * g.ck_n + B.base_off[j] + i;
+            entries[pos] = (uint32_t)pidx | (neg ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// exclusive scan of counts[0..n) into offsets[0..n], single CTA (n is at most a few 100k)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive(const uint32_t* counts, uint32_t* offsets, uint32_t n) {
+    __shared__ uint32_t part[1024];
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t per = (n + nth - 1) / nth;
+    const uint32_t lo = tid * per, hi = lo + per < n ? lo + per : n;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (uint32_t off = 1; off < nth; off <<= 1) {
+        uint32_t v = tid >= off ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = tid ? part[tid - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        offsets[i] = run;
+        run += counts[i];
+    }
+    if (tid == nth - 1) offsets[n] = part[nth - 1];
+}
+
+template <class FQ>
+APB_D void load_affine(const void* bases, uint64_t idx, Fp<FQ>& x, Fp<FQ>& y) {
+    x = load_fp<FQ>(bases, 2 * idx);
+    y = load_fp<FQ>(bases, 2 * idx + 1);
+}
+template <class FQ>
+APB_D XYZZ<FQ> load_xyzz(const void* arr, uint64_t idx) {
+    XYZZ<FQ> p;
+    p.x = load_fp<FQ>(arr, 4 * idx);
+    p.y = load_fp<FQ>(arr, 4 * idx + 1);
+    p.zz = load_fp<FQ>(arr, 4 * idx + 2);
+    p.zzz = load_fp<FQ>(arr, 4 * idx + 3);
+    return p;
+}
+template <class FQ>
+APB_D void store_xyzz(void* arr, uint64_t idx, const XYZZ<FQ>& p) {
+    store_fp<FQ>(arr, 4 * idx, p.x);
+    store_fp<FQ>(arr, 4 * idx + 1, p.y);
+    store_fp<FQ>(arr, 4 * idx + 2, p.zz);
+    store_fp<FQ>(arr, 4 * idx + 3, p.zzz);
+}
+
+// Each thread owns entries [t*E, (t+1)*E) of the bucket-sorted list.
+template <class FQ>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
+                                                        const void* bases, uint32_t E, void* bucket_sums, void* partials,
+                                                        int32_t* part_bucket) {
+    typedef Fp<FQ> F;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t M = offsets[nbuckets];
+    part_bucket[2 * t] = -1;
+    part_bucket[2 * t + 1] = -1;
+    uint64_t pos = t * E;
+    if (pos >= M) return;
+    const uint64_t end = pos + E < M ? pos + E : M;
+    // largest b with offsets[b] <= pos
+    uint32_t lo = 0, hi = nbuckets;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    while (offsets[b + 1] <= pos) b++;     // skip empty buckets sharing the same offset
+    while (pos < end) {
+        const uint64_t bstart = offsets[b], bend = offsets[b + 1];
+        const uint64_t run_start = pos, run_end = bend < end ? bend : end;
+        XYZZ<FQ> acc = XYZZ<FQ>::identity();
+        for (; pos < run_end; pos++) {
+            uint32_t e = entries[pos];
+            F px, py;
+            load_affine<FQ>(bases, e & 0x7fffffffu, px, py);
+            if (px.is_zero() && py.is_zero()) continue;          // point at infinity
+            if (e >> 31) py = py.neg();
+            acc.add_affine(px, py);
+        }
+        const bool head = run_start == bstart, tail = run_end == bend;
+        if (head && tail) {
+            store_xyzz<FQ>(bucket_sums, b, acc);
+        } else if (head) {          // bucket continues in the next chunk(s)
+            store_xyzz<FQ>(partials, 2 * t + 1, acc);
+            part_bucket[2 * t + 1] = (int32_t)b;
+        } else {                    // bucket began in an earlier chunk
+            store_xyzz<FQ>(partials, 2 * t, acc);
+            part_bucket[2 * t] = (int32_t)b;
+        }
+        if (pos < end) {
+            b++;
+            while (offsets[b + 1] <= pos) b++;
+        }
+    }
+}
+
+// stitch buckets that straddle chunk borders: the chunk holding the head piece sums the rest
+template <class FQ>
+__global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uint32_t E, uint64_t nthreads, void* bucket_sums,
+                                                    const void* partials, const int32_t* part_bucket) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const int32_t b = part_bucket[2 * t + 1];
+    if (b < 0) return;
+    XYZZ<FQ> acc = load_xyzz<FQ>(partials, 2 * t + 1);
+    const uint64_t bend = offsets[b + 1];
+    for (uint64_t u = t + 1; u * E < bend; u++) {
+        XYZZ<FQ> p = load_xyzz<FQ>(partials, 2 * u);
+        acc.add(p);
+    }
+    store_xyzz<FQ>(bucket_sums, b, acc);
+}
+
+// Tree-sum jobs: out[job] = sum over e < m of in[base + e*stride], restricted (selbit >= 0) to
+// entries whose weight (e + woff) has bit `selbit` set.
+struct TreeJob {
+    uint32_t base, stride, m, woff;
+    int32_t selbit;
+    uint32_t out;
+};
+
+template <class FQ>
+__global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, const TreeJob* jobs) {
+    __shared__ uint4 sm[128 * 12];       // 128 XYZZ points (4 * 48 bytes)
+    const TreeJob J = jobs[blockIdx.x];
+    const uint32_t tid = threadIdx.x;
+    XYZZ<FQ> acc = XYZZ<FQ>::identity();
+    for (uint32_t e = tid; e < J.m; e += 128) {
+        if (J.selbit >= 0 && !(((e + J.woff) >> J.selbit) & 1)) continue;
+        XYZZ<FQ> p = load_xyzz<FQ>(in, (uint64_t)J.base + (uint64_t)e * J.stride);
+        acc.add(p);
+    }
+    store_xyzz<FQ>(sm, tid, acc);
+    __syncthreads();
+    for (uint32_t s = 64; s >= 1; s >>= 1) {
+        if (tid < s) {
+            XYZZ<FQ> p = load_xyzz<FQ>(sm, tid + s);
+            acc.add(p);
+        }
+        __syncthreads();
+        if (tid < s) store_xyzz<FQ>(sm, tid, acc);
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz<FQ>(out, J.out, acc);
+}
+
+// a^(p-2)
+template <class FQ>
+__device__ __noinline__ Fp<FQ> fp_inverse(const Fp<FQ>& a) {
+    Fp<FQ> acc = Fp<FQ>::one(), base = a;
+    uint32_t e[FQ::N];
+#pragma unroll
+    for (int i = 0; i < FQ::N; i++) e[i] = FQ::mod(i);
+    {   // e = p - 2 with borrow propagation (the low limb of the BLS12-377 modulus is 1)
+        uint32_t borrow = 2;
+        for (int i = 0; i < FQ::N && borrow; i++) {
+            uint32_t nb = e[i] < borrow ? 1u : 0u;
+            e[i] -= borrow;
+            borrow = nb;
+        }
+    }
+    for (int i = 0; i < 32 * FQ::N; i++) {
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * base;
+        base = base.sqr();
+    }
+    return acc;
+}
+
+// copies[f*n + i] = 2^(step*f) * P_i as affine points, f = 0..F-1 (copy 0 is the input itself)
+template <class FQ>
+__global__ void __launch_bounds__(128) k_ck_precompute(void* bases, uint64_t n, uint32_t F, uint32_t step) {
+    typedef Fp<FQ> Fe;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe px, py;
+    load_affine<FQ>(bases, i, px, py);
+    if (px.is_zero() && py.is_zero()) {
+        for (uint32_t f = 1; f < F; f++) {
+            store_fp<FQ>(bases, 2 * (f * n + i), px);
+            store_fp<FQ>(bases, 2 * (f * n + i) + 1, py);
+        }
+        return;
+    }
+    XYZZ<FQ> pts[MAX_COPIES];
+    Fe prefix[MAX_COPIES];
+    XYZZ<FQ> cur;
+    cur.x = px; cur.y = py; cur.zz = Fe::one(); cur.zzz = Fe::one();
+    Fe run = Fe::one();
+    for (uint32_t f = 1; f < F; f++) {
+        for (uint32_t s = 0; s < step; s++) cur = cur.dbl();
+        pts[f] = cur;
+        prefix[f] = run;             // product of zzz of copies 1..f-1
+        run = run * cur.zzz;
+    }
+    Fe inv = fp_inverse<FQ>(run);
+    for (uint32_t f = F - 1; f >= 1; f--) {
+        Fe zinv = inv * prefix[f];   // 1 / zzz_f
+        inv = inv * pts[f].zzz;
+        Fe r = pts[f].zz * zinv;     // zz/zzz = 1/z
+        Fe ax = pts[f].x * r.sqr();
+        Fe ay = pts[f].y * zinv;
+        store_fp<FQ>(bases, 2 * (f * n + i), ax);
+        store_fp<FQ>(bases, 2 * (f * n + i) + 1, ay);
+    }
+}
+
+}  // namespace apb
+
+using namespace apb;
+
+static const uint32_t CK_MAGIC = 0x434b3031;
+
+struct apb_ck_s {
+    uint32_t magic;
+    int curve;
+    size_t n;
+    uint32_t F, step;
+    void* bases;                   // F * n affine points
+    // workspace (grown on demand)
+    void* d_scalars; size_t scalars_cap;
+    uint32_t *counts, *offsets, *cursors; size_t buckets_cap;
+    uint32_t* entries; size_t entries_cap;
+    void* bucket_sums; size_t sums_cap;
+    void* partials; int32_t* part_bucket; size_t partial_cap;
+    void *stage_a, *stage_b; size_t stage_cap;
+    TreeJob* jobs; size_t jobs_cap;
+    uint64_t* h_out; size_t h_out_cap;   // pinned
+    // cached job table key
+    uint32_t jobs_c, jobs_windows;
+    std::vector<TreeJob>* h_jobs_a;
+    std::vector<TreeJob>* h_jobs_b;
+};
+
+template <class T>
+static int grow(T** p, size_t* cap, size_t need_bytes) {
+    if (*cap >= need_bytes) return APB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need_bytes + need_bytes / 8 + 256;
+    cudaError_t e = cudaMalloc((void**)p, want);
+    if (e != cudaSuccess) return set_err(APB_ERR_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    *cap = want;
+    return APB_OK;
+}
+
+extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out) {
+    if (!out || (!xy && n)) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: bad curve %d", curve);
+    APB_REQUIRE_INIT();
+    apb_ck_s* ck = new apb_ck_s();
+    memset(ck, 0, sizeof(*ck));
+    ck->magic = CK_MAGIC;
+    ck->curve = curve;
+    ck->n = n;
+    // precompute geometry: 16-bit steps -> 16 copies (all digit positions share one bucket set);
+    // very large keys use 64-bit steps (4 copies, 4 effective windows) to bound memory.
+    size_t big = (size_t)1 << 24;
+    if (const char* e = getenv("APB_MSM_FULL_PRECOMP_MAX")) big = (size_t)atoll(e);
+    if (n <= big) { ck->step = 16; ck->F = 16; } else { ck->step = 64; ck->F = 4; }
+    if (const char* e = getenv("APB_MSM_STEP")) {
+        ck->step = (uint32_t)atoi(e);
+        ck->F = (256 + ck->step - 1) / ck->step;
+        if (ck->F > (uint32_t)MAX_COPIES) { delete ck; return set_err(APB_ERR_INVALID_ARG, "APB_MSM_STEP too small"); }
+    }
+    size_t bytes = (n ? n : 1) * ck->F * 96;
+    cudaError_t e = cudaMalloc(&ck->bases, bytes);
+    if (e != cudaSuccess) { delete ck; return set_err(APB_ERR_OOM, "apb_ck_upload: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    if (n) {
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases, xy, n * 96, cudaMemcpyHostToDevice, g_stream));
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)n, ck->F, ck->step);
+        else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)n, ck->F, ck->step);
+        APB_CHECK_LAUNCH();
+        APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    }
+    *out = ck;
+    return APB_OK;
+}
+
+extern "C" int apb_ck_size(apb_ck_t ck, size_t* n) {
+    if (!ck || ck->magic != CK_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_size: bad handle");
+    *n = ck->n;
+    return APB_OK;
+}
+
+extern "C" void apb_ck_free(apb_ck_t ck) {
+    if (!ck || ck->magic != CK_MAGIC) return;
+    // offsets / cursors / stage_b are interior pointers of counts / stage_a
+    cudaFree(ck->bases); cudaFree(ck->d_scalars); cudaFree(ck->counts);
+    cudaFree(ck->entries); cudaFree(ck->bucket_sums); cudaFree(ck->partials);
+    cudaFree(ck->part_bucket); cudaFree(ck->stage_a); cudaFree(ck->jobs);
+    if (ck->h_out) cudaFreeHost(ck->h_out);
+    delete ck->h_jobs_a;
+    delete ck->h_jobs_b;
+    ck->magic = 0;
+    delete ck;
+}
+
+// choose digit width: c*G == step.  Small inputs use narrow digits (few buckets to reduce).
+static void choose_geom(const apb_ck_s* ck, size_t max_len, MsmGeom& g, uint32_t scalar_bits) {
+    uint32_t c = ck->step >= 16 ? 16 : ck->step;
+    if (ck->step % 16 != 0) c = ck->step;
+    if (max_len <= 4096 && ck->step % 8 == 0) c = 8;
+    if (const char* e = getenv("APB_MSM_C")) {
+        uint32_t v = (uint32_t)atoi(e);
+        if (v >= 2 && v <= 20 && ck->step % v == 0) c = v;
+    }
+    g.c = c;
+    g.G = ck->step / c;
+    g.W = (scalar_bits + c - 1) / c;       // |s| < 2^(bits-1): top digit cannot carry out
+    g.hb = 1u << (c - 1);
+    g.ck_n = ck->n;
+}
+
+// job tables for the two tree stages, for `windows` bucket windows of 2^(c-1) buckets
+static bool build_jobs(apb_ck_s* ck, uint32_t c, uint32_t windows, uint32_t& a_bits, uint32_t& b_bits) {
+    b_bits = (c - 1) / 2;
+    a_bits = (c - 1) - b_bits;
+    if (ck->h_jobs_a && ck->jobs_c == c && ck->jobs_windows == windows) return false;
+    if (!ck->h_jobs_a) { ck->h_jobs_a = new std::vector<TreeJob>(); ck->h_jobs_b = new std::vector<TreeJob>(); }
+    ck->h_jobs_a->clear();
+    ck->h_jobs_b->clear();
+    const uint32_t R = 1u << a_bits, Cc = 1u << b_bits, hb = 1u << (c - 1);
+    const uint32_t per_a = R + Cc, per_b = a_bits + b_bits + 1;
+    for (uint32_t w = 0; w < windows; w++) {
+        for (uint32_t r = 0; r < R; r++) ck->h_jobs_a->push_back(TreeJob{w * hb + r * Cc, 1, Cc, 0, -1, w * per_a + r});
+        for (uint32_t cc = 0; cc < Cc; cc++) ck->h_jobs_a->push_back(TreeJob{w * hb + cc, Cc, R, 0, -1, w * per_a + R + cc});
+        // stage B reads stage A's output: rows weighted by hi (bits 0..a-1), columns by lo+1 (bits 0..b)
+        for (uint32_t k = 0; k < a_bits; k++) ck->h_jobs_b->push_back(TreeJob{w * per_a, 1, R, 0, (int32_t)k, w * per_b + k});
+        for (uint32_t k = 0; k <= b_bits; k++) ck->h_jobs_b->push_back(TreeJob{w * per_a + R, 1, Cc, 1, (int32_t)k, w * per_b + a_bits + k});
+    }
+    ck->jobs_c = c;
+    ck->jobs_windows = windows;
+    return true;
+}
+
+template <class CV>
+static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int mont, uint64_t* out_xyz) {
+    typedef typename CV::FR FR;
+    typedef typename CV::FQ FQ;
+    host::Group grp;
+    grp.f = host::Field::make<FQ>();
+    const host::Field& f = grp.f;
+
+    size_t max_len = 0, total = 0;
+    for (uint32_t j = 0; j < B.k; j++) { max_len = std::max<size_t>(max_len, B.len[j]); total += B.len[j]; }
+    auto write_identity = [&](uint32_t j) { memset(out_xyz + 18 * j, 0, 18 * 8); };
+    if (total == 0) {
+        for (uint32_t j = 0; j < B.k; j++) write_identity(j);
+        return APB_OK;
+    }
+    MsmGeom g;
+    choose_geom(ck, max_len, g, FR::BITS);
+    const uint32_t windows = B.k * g.G;
+    const uint32_t nbuckets = windows * g.hb;
+    const uint64_t Mmax = (uint64_t)total * g.W;
+    if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
+
+    // chunk size for the accumulate pass
+    uint64_t target_threads = (uint64_t)g_num_sms * 384;
+    uint32_t E = (uint32_t)((Mmax + target_threads - 1) / target_threads);
+    if (E < 8) E = 8;
+    if (const char* e = getenv("APB_MSM_CHUNK")) E = (uint32_t)atoi(e);
+    const uint64_t acc_threads = (Mmax + E - 1) / E;
+    const uint64_t acc_blocks = (acc_threads + 127) / 128;
+    const uint64_t acc_slots = acc_blocks * 128;
+
+    int rc;
+    if ((rc = grow(&ck->counts, &ck->buckets_cap, (size_t)(nbuckets + 1) * 4 * 3)) != APB_OK) return rc;
+    ck->offsets = ck->counts + (nbuckets + 1);
+    ck->cursors = ck->offsets + (nbuckets + 1);
+    if ((rc = grow(&ck->entries, &ck->entries_cap, (size_t)Mmax * 4)) != APB_OK) return rc;
+    if ((rc = grow(&ck->bucket_sums, &ck->sums_cap, (size_t)nbuckets * 192)) != APB_OK) return rc;
+    {
+        size_t need = acc_slots * 2 * 192;
+        size_t cap2 = ck->partial_cap;
+        if ((rc = grow(&ck->partials, &ck->partial_cap, need)) != APB_OK) return rc;
+        if (cap2 != ck->partial_cap) {
+            if (ck->part_bucket) cudaFree(ck->part_bucket);
+            ck->part_bucket = nullptr;
+            APB_CUDA_TRY(cudaMalloc((void**)&ck->part_bucket, ck->partial_cap / 192 * 4 + 64));
+        }
+    }
+    uint32_t a_bits, b_bits;
+    const bool jobs_new = build_jobs(ck, g.c, windows, a_bits, b_bits);
+    const uint32_t per_a = (1u << a_bits) + (1u << b_bits), per_b = a_bits + b_bits + 1;
+    {
+        size_t need_a = (size_t)windows * per_a * 192, need_b = (size_t)windows * per_b * 192;
+        size_t cap_a = ck->stage_cap;
+        if (cap_a < need_a + need_b) {
+            if (ck->stage_a) cudaFree(ck->stage_a);
+            ck->stage_a = nullptr;
+            ck->stage_cap = 0;
+            APB_CUDA_TRY(cudaMalloc(&ck->stage_a, need_a + need_b + 256));
+            ck->stage_cap = need_a + need_b;
+        }
+        ck->stage_b = (char*)ck->stage_a + need_a;
+    }
+    const size_t njobs_a = ck->h_jobs_a->size(), njobs_b = ck->h_jobs_b->size();
+    const size_t jobs_cap_before = ck->jobs_cap;
+    if ((rc = grow(&ck->jobs, &ck->jobs_cap, (njobs_a + njobs_b) * sizeof(TreeJob))) != APB_OK) return rc;
+    if (jobs_new || jobs_cap_before != ck->jobs_cap) {
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs, ck->h_jobs_a->data(), njobs_a * sizeof(TreeJob), cudaMemcpyHostToDevice, g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs + njobs_a, ck->h_jobs_b->data(), njobs_b * sizeof(TreeJob), cudaMemcpyHostToDevice, g_stream));
+    }
+    const size_t out_bytes = (size_t)windows * per_b * 192;
+    if (ck->h_out_cap < out_bytes) {
+        if (ck->h_out) cudaFreeHost(ck->h_out);
+        ck->h_out = nullptr;
+        APB_CUDA_TRY(cudaMallocHost((void**)&ck->h_out, out_bytes + 256));
+        ck->h_out_cap = out_bytes;
+    }
+
+    // 1. histogram  2. scan  3. scatter
+    APB_CUDA_TRY(cudaMemsetAsync(ck->counts, 0, (size_t)(nbuckets + 1) * 4 * 3, g_stream));
+    APB_CUDA_TRY(cudaMemsetAsync(ck->bucket_sums, 0, (size_t)nbuckets * 192, g_stream));
+    dim3 dgrid((unsigned)((max_len + 255) / 256), B.k);
+    auto k_hist = k_msm_digits<FR, 0>;
+    auto k_scatter = k_msm_digits<FR, 1>;
+    APB_KLAUNCH(k_hist, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
+    APB_KLAUNCH(k_scan_exclusive, 1, SCAN_THREADS, 0, (const uint32_t*)ck->counts, ck->offsets, nbuckets);
+    APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
+    // 4. accumulate  5. stitch
+    APB_KLAUNCH(k_msm_accumulate<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
+                (const void*)ck->partials, (const int32_t*)ck->part_bucket);
+    // 6. bucket reduction trees
+    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_a, 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs);
+    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_b, 128, 0, (const void*)ck->stage_a, ck->stage_b, (const TreeJob*)(ck->jobs + njobs_a));
+    APB_CHECK_LAUNCH();
+    APB_CUDA_TRY(cudaMemcpyAsync(ck->h_out, ck->stage_b, out_bytes, cudaMemcpyDeviceToHost, g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+
+    // 7. host epilogue: Horner over weight bits, fold windows, normalise
+    const host::Pt* V = reinterpret_cast<const host::Pt*>(ck->h_out);
+    for (uint32_t j = 0; j < B.k; j++) {
+        host::Pt total_pt;
+        grp.set_identity(total_pt);
+        for (int gw = (int)g.G - 1; gw >= 0; gw--) {
+            const host::Pt* v = V + (size_t)(j * g.G + gw) * per_b;
+            host::Pt rows, cols;
+            grp.set_identity(rows);
+            grp.set_identity(cols);
+            for (int k = (int)a_bits - 1; k >= 0; k--) { grp.dbl(rows, rows); grp.add(rows, rows, v[k]); }
+            for (int k = (int)b_bits; k >= 0; k--) { grp.dbl(cols, cols); grp.add(cols, cols, v[a_bits + k]); }
+            for (uint32_t s = 0; s < b_bits; s++) grp.dbl(rows, rows);      // hi * 2^b
+            grp.add(rows, rows, cols);
+            for (uint32_t s = 0; s < g.c; s++) grp.dbl(total_pt, total_pt);
+            grp.add(total_pt, total_pt, rows);
+        }
+        uint64_t* o = out_xyz + 18 * j;
+        uint64_t ax[6], ay[6];
+        if (!grp.to_affine(ax, ay, total_pt)) { write_identity(j); continue; }
+        memcpy(o, ax, 48);
+        memcpy(o + 6, ay, 48);
+        memcpy(o + 12, f.one, 48);
+    }
+    return APB_OK;
+}
+
+static int msm_dispatch(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int mont, uint64_t* out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, g_stream);
+    int rc = ck->curve == APB_CURVE_BLS12_381 ? run_msm<Curve381>(ck, B, d_scalars, mont, out)
+                                               : run_msm<Curve377>(ck, B, d_scalars, mont, out);
+    cudaEventRecord(e1, g_stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    g_last_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scalars, const size_t* base_offsets,
+                             const size_t* lens, int mont, uint64_t* out_xyz) {
+    if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm: bad key handle");
+    if (k == 0) return APB_OK;
+    if (!scalars || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm: null argument");
+    for (size_t done = 0; done < k; done += MAX_BATCH) {
+        MsmBatch B;
+        memset(&B, 0, sizeof(B));
+        B.k = (uint32_t)std::min<size_t>(MAX_BATCH, k - done);
+        size_t total = 0;
+        for (uint32_t j = 0; j < B.k; j++) {
+            size_t off = base_offsets ? base_offsets[done + j] : 0, len = lens[done + j];
+            if (off + len > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm: %zu scalars at base offset %zu exceed the %zu resident powers", len, off, ck->n);
+            if (len && !scalars[done + j]) return set_err(APB_ERR_INVALID_ARG, "apb_msm: null scalars");
+            B.scal_off[j] = total;
+            B.base_off[j] = off;
+            B.len[j] = len;
+            total += len;
+        }
+        int rc = grow(&ck->d_scalars, &ck->scalars_cap, (total ? total : 1) * 32);
+        if (rc != APB_OK) return rc;
+        for (uint32_t j = 0; j < B.k; j++)
+            if (B.len[j])
+                APB_CUDA_TRY(cudaMemcpyAsync((char*)ck->d_scalars + B.scal_off[j] * 32, scalars[done + j], B.len[j] * 32, cudaMemcpyHostToDevice, g_stream));
+        rc = msm_dispatch(ck, B, ck->d_scalars, mont, out_xyz + 18 * done);
+        if (rc != APB_OK) return rc;
+    }
+    return APB_OK;
+}
+
+extern "C" int apb_msm(apb_ck_t ck, size_t base_offset, const uint64_t* scalars, size_t n, int mont, uint64_t out_xyz[18]) {
+    const uint64_t* sp[1] = {scalars};
+    size_t off[1] = {base_offset}, len[1] = {n};
+    return apb_msm_batch(ck, 1, sp, off, len, mont, out_xyz);
+}
+
+extern "C" int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalars, size_t n, int mont, uint64_t out_xyz[18]) {
+    if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_dev: bad key handle");
+    if (!out_xyz || (n && !d_scalars)) return set_err(APB_ERR_INVALID_ARG, "apb_msm_dev: null argument");
+    if (base_offset + n > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm_dev: %zu scalars at base offset %zu exceed the %zu resident powers", n, base_offset, ck->n);
+    MsmBatch B;
+    memset(&B, 0, sizeof(B));
+    B.k = 1;
+    B.base_off[0] = base_offset;
+    B.len[0] = n;
+    return msm_dispatch(ck, B, d_scalars, mont, out_xyz);
+}
+
+// d_scalars: one device buffer; scal_offs in elements
+extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t* scal_offs, const size_t* base_offsets,
+                                 const size_t* lens, int mont, uint64_t* out_xyz) {
+    if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_batch_dev: bad key handle");
+    if (k == 0) return APB_OK;
+    if (!d_scalars || !scal_offs || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm_batch_dev: null argument");
+    for (size_t done = 0; done < k; done += MAX_BATCH) {
+        MsmBatch B;
+        memset(&B, 0, sizeof(B));
+        B.k = (uint32_t)std::min<size_t>(MAX_BATCH, k - done);
+        for (uint32_t j = 0; j < B.k; j++) {
+            size_t off = base_offsets ? base_offsets[done + j] : 0, len = lens[done + j];
+            if (off + len > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm: %zu scalars at base offset %zu exceed the %zu resident powers", len, off, ck->n);
+            B.scal_off[j] = scal_offs[done + j];
+            B.base_off[j] = off;
+            B.len[j] = len;
+        }
+        int rc = msm_dispatch(ck, B, d_scalars, mont, out_xyz + 18 * done);
+        if (rc != APB_OK) return rc;
+    }
+    return APB_OK;
+}
+
+extern "C" int apb_g1_compress(int curve, const uint64_t xyz[18], uint8_t out[48]) {
+    if (!xyz || !out) return set_err(APB_ERR_INVALID_ARG, "apb_g1_compress: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_g1_compress: bad curve");
+    host::Field f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fq381>() : host::Field::make<Fq377>();
+    memset(out, 0, 48);
+    if (f.is_zero(xyz + 12)) { out[47] |= 0x40; return APB_OK; }
+    uint64_t x[6], y[6], ny[6];
+    if (f.eq(xyz + 12, f.one)) {
+        f.to_canonical(x, xyz);
+        f.to_canonical(y, xyz + 6);
+    } else {       // general Jacobian input: x = X/Z^2, y = Y/Z^3
+        uint64_t zi[6], zi2[6], zi3[6], t[6];
+        f.inv(zi, xyz + 12);
+        f.sqr(zi2, zi);
+        f.mul(zi3, zi2, zi);
+        f.mul(t, xyz, zi2);
+        f.to_canonical(x, t);
+        f.mul(t, xyz + 6, zi3);
+        f.to_canonical(y, t);
+    }
+    // ny = p - y (canonical); flag = y > ny
+    uint64_t borrow = 0;
+    for (int i = 0; i < 6; i++) {
+        host::u128 d = (host::u128)f.mod[i] - y[i] - borrow;
+        ny[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    bool y_is_larger = false;
+    for (int i = 5; i >= 0; i--) {
+        if (y[i] != ny[i]) { y_is_larger = y[i] > ny[i]; break; }
+    }
+    memcpy(out, x, 48);
+    if (y_is_larger) out[47] |= 0x80;
+    return APB_OK;
+}

@@ -1,0 +1,418 @@
+// Radix-2^k number-theoretic transforms over Fr (BLS12-381 / BLS12-377) for sm_100a.
+//
+// Replaces ark_poly 0.3 Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft} as called
+// by plonk-core (prover.rs:197-203,241,282,303,305; quotient_poly.rs:72-120,176,205,294,325;
+// permutation/mod.rs:199-205,671-674,751,800; pi.rs:115; lookup/multiset.rs:201;
+// preprocess.rs:145-210,304-340).  Same semantics: input zero-extended to N, natural order in
+// and out, coset shift g = Fr::multiplicative_generator(), inverse scaled by 1/N.
+//
+// Algorithm (not arkworks' in-place radix-2 + bit-reversal): an autosorting mixed-radix
+// decomposition N = N1*N2(*N3).  Pass p transforms digit p of the index inside shared memory
+// (tile = N_p points x C adjacent columns so that every global access is a run of C*32 B),
+// multiplies by the inter-pass twiddle w_N^(lo * k_p * M_p) from the resident table, and the
+// last pass writes to the digit-reversed position, so the result lands in natural order
+// without a separate permutation pass.  The coset pre-scale (g^i, only on the in_len supplied
+// coefficients), zero-extension (no loads of implied zeros), 1/N and g^-i post-scales are
+// fused into the first / last pass.  HBM traffic: P reads + P writes of the vector (P = 2 up
+// to 2^20, 3 up to 2^30); for N <= 2^21 the vector is L2-resident between passes.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "host_ec.hpp"
+
+namespace apb {
+
+static const int COSET_LO_BITS = 10;
+
+struct NttPassArgs {
+    const void* in;
+    void* out;
+    uint64_t in_batch_stride, out_batch_stride;   // elements
+    uint32_t log_n, log_t, log_c;
+    uint64_t na, in_a, in_b, out_a, out_b;
+    uint64_t in_sd, in_sc, out_sk, out_sc;
+    const void* roots;        // w^i (or w^-i), i < N/2
+    uint64_t tw_mult;         // inter-pass twiddle exponent multiplier; 0 = none
+    uint64_t in_len;          // first pass: elements >= in_len are zero (no load); else ~0
+    const void* pre_lo;       // first pass coset pre-scale tables (g^j, g^(j<<10)) or null
+    const void* pre_hi;
+    const void* post_lo;      // last pass post-scale: lo/hi tables (coset_ifft) ...
+    const void* post_hi;
+    int post_const;           // ... or the constant 1/N (ifft)
+    uint32_t size_inv[8];
+};
+
+template <class FR>
+APB_D Fp<FR> smem_get(const uint4* lo, const uint4* hi, uint32_t i) {
+    Fp<FR> r;
+    uint4 a = lo[i], b = hi[i];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class FR>
+APB_D void smem_put(uint4* lo, uint4* hi, uint32_t i, const Fp<FR>& a) {
+    lo[i] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    hi[i] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+// One pass over one tile.  Shared memory: data planes (2 x T*C uint4) + root planes (2 x T/2).
+template <class FR>
+__global__ void __launch_bounds__(512) k_ntt_pass(NttPassArgs A) {
+    typedef Fp<FR> F;
+    APB_DYN_SMEM(smem);
+    const uint32_t T = 1u << A.log_t, C = 1u << A.log_c, TC = T << A.log_c;
+    uint4* xlo = reinterpret_cast<uint4*>(smem);
+    uint4* xhi = xlo + TC;
+    uint4* wlo = xhi + TC;
+    uint4* whi = wlo + (T >> 1);
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint64_t tile = blockIdx.x;
+    const uint64_t ta = tile % A.na, tb = tile / A.na;
+    const uint64_t base_in = ta * A.in_a + tb * A.in_b;
+    const uint64_t base_out = ta * A.out_a + tb * A.out_b;
+    const uint4* in = reinterpret_cast<const uint4*>(A.in) + 2 * A.in_batch_stride * blockIdx.y;
+    uint4* out = reinterpret_cast<uint4*>(A.out) + 2 * A.out_batch_stride * blockIdx.y;
+
+    // roots of the tile transform: w_T^j = w_N^(j * N/T)
+    for (uint32_t j = tid; j < (T >> 1); j += nth) {
+        F w = load_fp<FR>(A.roots, (uint64_t)j << (A.log_n - A.log_t));
+        smem_put<FR>(wlo, whi, j, w);
+    }
+    // load (zero-extension and coset pre-scale fused)
+    for (uint32_t e = tid; e < TC; e += nth) {
+        uint32_t c = e & (C - 1), d = e >> A.log_c;
+        uint64_t idx = base_in + d * A.in_sd + c * A.in_sc;
+        F v;
+        if (idx < A.in_len) {
+            v = load_fp<FR>(in, idx);
+            if (A.pre_lo) {
+                F s = load_fp<FR>(A.pre_lo, idx & ((1u << COSET_LO_BITS) - 1)) * load_fp<FR>(A.pre_hi, idx >> COSET_LO_BITS);
+                v = v * s;
+            }
+        } else {
+            v = F::zero();
+        }
+        smem_put<FR>(xlo, xhi, e, v);
+    }
+    __syncthreads();
+
+    // decimation-in-frequency stages; result index k sits at bit-reversed row
+    for (uint32_t lh = A.log_t; lh-- > 0;) {
+        const uint32_t h = 1u << lh;
+        for (uint32_t b = tid; b < (TC >> 1); b += nth) {
+            uint32_t c = b & (C - 1), r = b >> A.log_c;
+            uint32_t j = r & (h - 1), blk = r >> lh;
+            uint32_t i0 = (((blk << (lh + 1)) + j) << A.log_c) + c;
+            uint32_t i1 = i0 + (h << A.log_c);
+            F u = smem_get<FR>(xlo, xhi, i0), v = smem_get<FR>(xlo, xhi, i1);
+            smem_put<FR>(xlo, xhi, i0, u + v);
+            F t = u - v;
+            if (lh > 0) t = t * smem_get<FR>(wlo, whi, j << (A.log_t - 1 - lh));
+            smem_put<FR>(xlo, xhi, i1, t);
+        }
+        __syncthreads();
+    }
+
+    // store (inter-pass twiddle / final scaling fused)
+    const uint64_t half_n = (uint64_t)1 << (A.log_n - 1);
+    for (uint32_t e = tid; e < TC; e += nth) {
+        uint32_t c = e & (C - 1), k = e >> A.log_c;
+        uint32_t row = A.log_t ? (__brev(k) >> (32 - A.log_t)) : 0;
+        F v = smem_get<FR>(xlo, xhi, (row << A.log_c) + c);
+        uint64_t oidx = base_out + k * A.out_sk + c * A.out_sc;
+        if (A.tw_mult) {
+            uint64_t ex = (ta * C + c) * k * A.tw_mult;
+            if (ex != 0) {
+                F w = (ex < half_n) ? load_fp<FR>(A.roots, ex) : load_fp<FR>(A.roots, ex - half_n).neg();
+                v = v * w;
+            }
+        }
+        if (A.post_lo) {
+            F s = load_fp<FR>(A.post_lo, oidx & ((1u << COSET_LO_BITS) - 1)) * load_fp<FR>(A.post_hi, oidx >> COSET_LO_BITS);
+            v = v * s;
+        } else if (A.post_const) {
+            F s;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s.v[i] = A.size_inv[i];
+            v = v * s;
+        }
+        store_fp<FR>(out, oidx, v);
+    }
+}
+
+// out[i] = scale * base^(i << shift), base^(2^k) given in pow2[k]
+template <class FR>
+__global__ void k_pow_table(void* out, uint64_t count, const void* pow2, uint32_t shift, const void* scale) {
+    typedef Fp<FR> F;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    F acc = load_fp<FR>(scale, 0);
+    uint64_t e = i << shift;
+    for (int k = 0; e != 0; k++, e >>= 1)
+        if (e & 1) acc = acc * load_fp<FR>(pow2, k);
+    store_fp<FR>(out, i, acc);
+}
+
+}  // namespace apb
+
+using namespace apb;
+
+struct apb_domain_s {
+    uint32_t magic;
+    int curve;
+    uint32_t log_n;
+    size_t n;
+    void *tw, *itw;                       // N/2 each
+    void *clo, *chi, *iclo, *ichi;        // coset tables
+    void* scratch;
+    size_t scratch_elems;
+    uint32_t size_inv[8];
+    int npass;
+    uint32_t lbits[3];
+};
+static const uint32_t DOMAIN_MAGIC = 0x444f4d31;
+
+template <class FR>
+static int build_tables(apb_domain_s* d) {
+    host::Field f = host::Field::make<FR>();
+    const uint32_t L = d->log_n;
+    // w = two_adic_root ^ (2^(adicity - L))
+    uint64_t w[4], winv[4], g[4], ginv[4], ninv[4], nval[4];
+    for (int i = 0; i < 4; i++) {
+        w[i] = (uint64_t)FR::two_adic_root_mont(2 * i) | ((uint64_t)FR::two_adic_root_mont(2 * i + 1) << 32);
+        g[i] = (uint64_t)FR::generator_mont(2 * i) | ((uint64_t)FR::generator_mont(2 * i + 1) << 32);
+        ginv[i] = (uint64_t)FR::generator_inv_mont(2 * i) | ((uint64_t)FR::generator_inv_mont(2 * i + 1) << 32);
+    }
+    for (uint32_t i = L; i < (uint32_t)FR::TWO_ADICITY; i++) f.sqr(w, w);
+    f.inv(winv, w);
+    // 1/N in Montgomery form: N as field element = 2^L
+    f.set(nval, f.one);
+    for (uint32_t i = 0; i < L; i++) f.dbl(nval, nval);
+    f.inv(ninv, nval);
+    for (int i = 0; i < 4; i++) { d->size_inv[2 * i] = (uint32_t)ninv[i]; d->size_inv[2 * i + 1] = (uint32_t)(ninv[i] >> 32); }
+
+    uint64_t* h_pow2 = (uint64_t*)malloc(4 * 64 * 8 * 4);      // 4 bases x 64 powers
+    const uint64_t* bases[4] = {w, winv, g, ginv};
+    for (int b = 0; b < 4; b++) {
+        uint64_t cur[4];
+        f.set(cur, bases[b]);
+        for (int k = 0; k < 64; k++) {
+            memcpy(h_pow2 + (b * 64 + k) * 4, cur, 32);
+            f.sqr(cur, cur);
+        }
+    }
+    void* d_pow2 = nullptr;
+    void* d_scale = nullptr;
+    APB_CUDA_TRY(cudaMalloc(&d_pow2, 4 * 64 * 32));
+    APB_CUDA_TRY(cudaMalloc(&d_scale, 64));
+    APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2, 4 * 64 * 32, cudaMemcpyHostToDevice, g_stream));
+    uint64_t scales[8];
+    memcpy(scales, f.one, 32);
+    memcpy(scales + 4, ninv, 32);
+    APB_CUDA_TRY(cudaMemcpyAsync(d_scale, scales, 64, cudaMemcpyHostToDevice, g_stream));
+
+    const size_t half = d->n > 1 ? d->n / 2 : 1;
+    const size_t nhi = (d->n >> COSET_LO_BITS) + 1, nlo = (size_t)1 << COSET_LO_BITS;
+    APB_CUDA_TRY(cudaMalloc(&d->tw, half * 32));
+    APB_CUDA_TRY(cudaMalloc(&d->itw, half * 32));
+    APB_CUDA_TRY(cudaMalloc(&d->clo, nlo * 32));
+    APB_CUDA_TRY(cudaMalloc(&d->iclo, nlo * 32));
+    APB_CUDA_TRY(cudaMalloc(&d->chi, nhi * 32));
+    APB_CUDA_TRY(cudaMalloc(&d->ichi, nhi * 32));
+    const char* p2 = (const char*)d_pow2;
+    const char* sc = (const char*)d_scale;
+    auto blocks = [](size_t c) { return (unsigned)((c + 127) / 128); };
+    APB_KLAUNCH(k_pow_table<FR>, blocks(half), 128, 0, d->tw, (uint64_t)half, (const void*)(p2 + 0 * 64 * 32), 0u, (const void*)sc);
+    APB_KLAUNCH(k_pow_table<FR>, blocks(half), 128, 0, d->itw, (uint64_t)half, (const void*)(p2 + 1 * 64 * 32), 0u, (const void*)sc);
+    APB_KLAUNCH(k_pow_table<FR>, blocks(nlo), 128, 0, d->clo, (uint64_t)nlo, (const void*)(p2 + 2 * 64 * 32), 0u, (const void*)sc);
+    APB_KLAUNCH(k_pow_table<FR>, blocks(nhi), 128, 0, d->chi, (uint64_t)nhi, (const void*)(p2 + 2 * 64 * 32), (uint32_t)COSET_LO_BITS, (const void*)sc);
+    APB_KLAUNCH(k_pow_table<FR>, blocks(nlo), 128, 0, d->iclo, (uint64_t)nlo, (const void*)(p2 + 3 * 64 * 32), 0u, (const void*)sc);
+    // 1/N folded into the high table of the inverse coset scale
+    APB_KLAUNCH(k_pow_table<FR>, blocks(nhi), 128, 0, d->ichi, (uint64_t)nhi, (const void*)(p2 + 3 * 64 * 32), (uint32_t)COSET_LO_BITS, (const void*)(sc + 32));
+    APB_CHECK_LAUNCH();
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    cudaFree(d_pow2);
+    cudaFree(d_scale);
+    free(h_pow2);
+    return APB_OK;
+}
+
+static void plan_passes(apb_domain_s* d) {
+    int maxbits = 10;
+    if (const char* e = getenv("APB_NTT_MAX_LOG_TILE")) maxbits = atoi(e);
+    if (maxbits < 1) maxbits = 1;
+    if (maxbits > 10) maxbits = 10;
+    uint32_t L = d->log_n;
+    int P = L == 0 ? 1 : (int)((L + maxbits - 1) / maxbits);
+    if (P > 3) P = 3;     // log_n <= 30 enforced by apb_domain_new
+    d->npass = P;
+    for (int i = 0; i < P; i++) d->lbits[i] = L / P + ((uint32_t)i < L % P ? 1 : 0);
+}
+
+extern "C" int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out) {
+    if (!out) return set_err(APB_ERR_INVALID_ARG, "apb_domain_new: null out");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_domain_new: bad curve %d", curve);
+    uint32_t adicity = curve == APB_CURVE_BLS12_381 ? (uint32_t)Fr381::TWO_ADICITY : (uint32_t)Fr377::TWO_ADICITY;
+    if (log_n > adicity || log_n > 30) return set_err(APB_ERR_DOMAIN_TOO_LARGE, "apb_domain_new: log_n %u exceeds supported size", log_n);
+    APB_REQUIRE_INIT();
+    apb_domain_s* d = new apb_domain_s();
+    memset(d, 0, sizeof(*d));
+    d->magic = DOMAIN_MAGIC;
+    d->curve = curve;
+    d->log_n = log_n;
+    d->n = (size_t)1 << log_n;
+    plan_passes(d);
+    int rc = curve == APB_CURVE_BLS12_381 ? build_tables<Fr381>(d) : build_tables<Fr377>(d);
+    if (rc != APB_OK) { apb_domain_free(d); return rc; }
+    *out = d;
+    return APB_OK;
+}
+
+extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
+    if (!d || d->magic != DOMAIN_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_domain_size: bad handle");
+    *n = d->n;
+    return APB_OK;
+}
+
+extern "C" void apb_domain_free(apb_domain_t d) {
+    if (!d || d->magic != DOMAIN_MAGIC) return;
+    cudaFree(d->tw); cudaFree(d->itw); cudaFree(d->clo); cudaFree(d->chi);
+    cudaFree(d->iclo); cudaFree(d->ichi); cudaFree(d->scratch);
+    d->magic = 0;
+    delete d;
+}
+
+template <class FR>
+static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, uint64_t in_stride, void* d_out,
+                   uint64_t out_stride, size_t batch) {
+    const bool inverse = kind == APB_NTT_IFFT || kind == APB_NTT_COSET_IFFT;
+    const uint32_t L = d->log_n;
+    const int P = d->npass;
+    int log_cols_max = 4;
+    if (const char* e = getenv("APB_NTT_LOG_COLS")) log_cols_max = atoi(e);
+    if (P > 1 && d->scratch_elems < d->n * batch) {
+        cudaFree(d->scratch);
+        d->scratch = nullptr;
+        d->scratch_elems = 0;
+        APB_CUDA_TRY(cudaMalloc(&d->scratch, d->n * batch * 32));
+        d->scratch_elems = d->n * batch;
+    }
+    uint32_t sbits = L;      // log2(S_p) running
+    uint32_t mbits = 0;      // log2(M_p)
+    for (int p = 0; p < P; p++) {
+        const uint32_t lt = d->lbits[p];
+        sbits -= lt;
+        NttPassArgs A;
+        memset(&A, 0, sizeof(A));
+        A.log_n = L;
+        A.log_t = lt;
+        const bool first = p == 0, last = p == P - 1;
+        A.in = first ? d_in : d->scratch;
+        A.out = last ? d_out : d->scratch;
+        A.in_batch_stride = first ? in_stride : d->n;
+        A.out_batch_stride = last ? out_stride : d->n;
+        A.roots = inverse ? d->itw : d->tw;
+        A.in_len = first ? in_len : ~(uint64_t)0;
+        // columns: keep T*C <= 4096 elements (128 KB of shared memory)
+        uint32_t lc = 12 > lt ? 12 - lt : 0;
+        if ((int)lc > log_cols_max) lc = log_cols_max;
+        if (!last) {
+            if (lc > sbits) lc = sbits;
+            A.log_c = lc;
+            A.na = (uint64_t)1 << (sbits - lc);
+            A.in_a = A.out_a = (uint64_t)1 << lc;
+            A.in_b = A.out_b = (uint64_t)1 << (sbits + lt);
+            A.in_sd = A.out_sk = (uint64_t)1 << sbits;
+            A.in_sc = A.out_sc = 1;
+            A.tw_mult = (uint64_t)1 << mbits;
+        } else if (P == 1) {
+            A.log_c = 0;
+            A.na = 1;
+            A.in_sd = A.out_sk = 1;
+            A.in_sc = A.out_sc = 1;
+        } else {
+            const uint32_t l1 = d->lbits[0];
+            const uint32_t s1 = L - l1;              // log2(S_1)
+            if (lc > l1) lc = l1;
+            A.log_c = lc;
+            A.na = (uint64_t)1 << (l1 - lc);
+            A.in_a = (uint64_t)1 << (lc + s1);
+            A.in_b = (uint64_t)1 << lt;
+            A.in_sd = 1;
+            A.in_sc = (uint64_t)1 << s1;
+            A.out_a = (uint64_t)1 << lc;
+            A.out_b = (uint64_t)1 << l1;
+            A.out_sk = (uint64_t)1 << mbits;
+            A.out_sc = 1;
+        }
+        if (first && kind == APB_NTT_COSET_FFT) { A.pre_lo = d->clo; A.pre_hi = d->chi; }
+        if (last && kind == APB_NTT_COSET_IFFT) { A.post_lo = d->iclo; A.post_hi = d->ichi; }
+        if (last && kind == APB_NTT_IFFT) { A.post_const = 1; memcpy(A.size_inv, d->size_inv, 32); }
+        const uint64_t tiles = d->n >> (lt + A.log_c);
+        const uint32_t tc = 1u << (lt + A.log_c);
+        uint32_t threads = tc / 2;
+        if (threads < 32) threads = 32;
+        if (threads > 512) threads = 512;
+        const size_t smem = (size_t)tc * 32 + (size_t)(1u << lt) * 16 + 64;
+        static size_t smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<Fr381>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<Fr377>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            smem_set = 200 * 1024;
+        }
+        APB_KLAUNCH(k_ntt_pass<FR>, dim3((unsigned)tiles, (unsigned)batch), threads, smem, A);
+        mbits += lt;
+    }
+    APB_CHECK_LAUNCH();
+    return APB_OK;
+}
+
+extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, size_t in_stride, void* d_out,
+                                 size_t out_stride, size_t batch, int sync) {
+    if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
+    if (kind < 0 || kind > 3) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: bad kind %d", kind);
+    if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
+    if (batch == 0) return APB_OK;
+    if (!d_out || (!d_in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
+    int rc = d->curve == APB_CURVE_BLS12_381
+                 ? run_ntt<Fr381>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch)
+                 : run_ntt<Fr377>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch);
+    if (rc != APB_OK) return rc;
+    if (sync) APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+
+extern "C" int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void* d_out, int sync) {
+    if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
+    return apb_ntt_batch_dev(d, kind, d_in, in_len, d->n, d_out, d->n, 1, sync);
+}
+
+extern "C" int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_len, uint64_t* out) {
+    if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
+    if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
+    if (!out || (!in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
+    void *d_in = nullptr, *d_out = nullptr;
+    APB_CUDA_TRY(cudaMalloc(&d_in, (in_len ? in_len : 1) * 32));
+    APB_CUDA_TRY(cudaMalloc(&d_out, d->n * 32));
+    if (in_len) APB_CUDA_TRY(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, g_stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, g_stream);
+    int rc = apb_ntt_dev(d, kind, d_in, in_len, d_out, 0);
+    cudaEventRecord(e1, g_stream);
+    if (rc == APB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, d->n * 32, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc = set_err(APB_ERR_CUDA, "apb_ntt: %s", cudaGetErrorString(e));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        g_last_ms = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}

@@ -1,0 +1,137 @@
+/*
+ * apb.h - C ABI of the B200-native proving hot path of heliaxdev/ark-plonk.
+ *
+ * This is the boundary a Rust `apb-sys` crate would bind.  Each entry
+ * point cites the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - Field elements cross the boundary as little-endian u64 limbs in MONTGOMERY form
+ *     (R = 2^256 for Fr, 2^384 for Fq): byte-identical to arkworks 0.3 `Fp256` / `Fp384`
+ *     in-memory limbs.  MSM scalars may also be passed canonical (what `into_repr()` yields).
+ *   - G1 affine bases are packed 96-byte records x || y (6+6 u64, Montgomery).  The point at
+ *     infinity is the record of all zero bytes (arkworks keeps an out-of-band `infinity` flag).
+ *   - Every function returns an `apb_status`; nothing unwinds across the boundary;
+ *     `apb_last_error()` gives a thread-local message.
+ *   - Handles own device memory (bases, twiddles) which stays resident in HBM until freed.
+ *   - `_dev` variants take device pointers and enqueue on the handle's stream without a host
+ *     synchronisation; the plain variants block until results are in host memory (the
+ *     semantics of the reference's synchronous Rust calls).
+ *   - One process drives one GPU (`apb_init(device)`); multi-GPU sharding is done by the
+ *     host layer with one process per GPU.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     APB_ERR_CUDA.
+ */
+#ifndef APB_H
+#define APB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    APB_OK = 0,
+    APB_ERR_INVALID_ARG = 1,     /* null pointer, bad enum, bad length */
+    APB_ERR_TOO_MANY_COEFFS = 2, /* ark-poly-commit Error::TooManyCoefficients (plonk-core/src/error.rs:96-107) */
+    APB_ERR_DOMAIN_TOO_LARGE = 3,/* log_n > TWO_ADICITY (plonk-core/src/proof_system/prover.rs:169-173 -> Error::InvalidEvalDomainSize) */
+    APB_ERR_BAD_HANDLE = 4,
+    APB_ERR_CUDA = 5,            /* CUDA runtime error or no device */
+    APB_ERR_OOM = 6
+} apb_status;
+
+/* curve / field selectors: the test matrix of plonk-core/src/test.rs:84-115 */
+#define APB_CURVE_BLS12_381 0
+#define APB_CURVE_BLS12_377 1
+
+/* transform kinds: ark_poly::EvaluationDomain::{fft, ifft, coset_fft, coset_ifft} */
+#define APB_NTT_FFT 0
+#define APB_NTT_IFFT 1
+#define APB_NTT_COSET_FFT 2
+#define APB_NTT_COSET_IFFT 3
+
+typedef struct apb_ck_s* apb_ck_t;          /* resident CommitterKey powers (SonicKZG10 CommitterKey::powers_of_g) */
+typedef struct apb_domain_s* apb_domain_t;  /* resident Radix2EvaluationDomain (twiddles) */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int apb_init(int device);                   /* idempotent; binds this process to one GPU */
+const char* apb_last_error(void);
+const char* apb_version(void);
+
+/* ---- commitment key: replaces PC::trim + CommitterKey (plonk-core/src/circuit.rs:236,276,310) */
+/* xy: n packed affine points (12 u64 each, Montgomery).  Uploaded once; a table of 2^(c*k)
+ * multiples may be precomputed on the device (see DESIGN.md "MSM"). */
+int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out);
+int apb_ck_size(apb_ck_t ck, size_t* n);
+void apb_ck_free(apb_ck_t ck);
+
+/* ---- MSM: replaces ark_ec::msm::VariableBaseMSM::multi_scalar_mul
+ *      (plonk-core/src/commitment.rs:45; inside KZG10::commit/open reached from
+ *       plonk-core/src/proof_system/prover.rs:213,290,313,316,362,388,459,579,582,606,609) */
+/* result = sum_{i<n} scalars[i] * bases[base_offset + i], returned as a normalised Jacobian
+ * point X,Y,Z (Z = 1 in Montgomery form, or X=Y=Z=0.. with Z == 0 for the identity).
+ * scalars: n x 4 u64; `scalars_are_montgomery` != 0 -> Fr Montgomery limbs (polynomial
+ * coefficients as stored), else canonical integers < r.  n == 0 is valid (identity). */
+int apb_msm(apb_ck_t ck, size_t base_offset, const uint64_t* scalars, size_t n,
+            int scalars_are_montgomery, uint64_t out_xyz[18]);
+/* k independent MSMs over the same key in one pass (PC::commit of several polynomials,
+ * e.g. the 4 wire polynomials at prover.rs:213).  out: k x 18 u64. */
+int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scalars, const size_t* base_offsets,
+                  const size_t* lens, int scalars_are_montgomery, uint64_t* out_xyz);
+/* device-resident scalars (e.g. an ifft result that never left HBM) */
+int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalars, size_t n,
+                int scalars_are_montgomery, uint64_t out_xyz[18]);
+
+/* k MSMs whose scalars already sit in ONE device buffer; scal_offs are element offsets into it */
+int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t* scal_offs,
+                      const size_t* base_offsets, const size_t* lens, int scalars_are_montgomery,
+                      uint64_t* out_xyz);
+
+/* ark-serialize compressed G1Affine (48 bytes; flags in the top bits of the last byte):
+ * what `Commitment` contributes to the transcript (plonk-core/src/transcript.rs:27-33). */
+int apb_g1_compress(int curve, const uint64_t xyz[18], uint8_t out[48]);
+
+/* ---- evaluation domain: replaces ark_poly::GeneralEvaluationDomain / Radix2EvaluationDomain
+ *      (constructed at prover.rs:169, preprocess.rs:284, quotient_poly.rs:43-47) */
+int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out);
+int apb_domain_size(apb_domain_t d, size_t* n);
+void apb_domain_free(apb_domain_t d);
+
+/* fft / ifft / coset_fft / coset_ifft (call sites: prover.rs:197-203,241,282,303,305;
+ * quotient_poly.rs:72-120,176,205,294,325; permutation/mod.rs:199-205,671-674,751,800;
+ * pi.rs:115; lookup/multiset.rs:201; preprocess.rs:145-210,304-340).
+ * in: in_len <= N elements (4 u64 each, Montgomery), implicitly zero-extended to N;
+ * out: N elements, natural order.  in_len == 0 gives N zeros. */
+int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_len, uint64_t* out);
+/* device pointers; d_in may equal d_out; asynchronous on the domain's stream unless sync != 0 */
+int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void* d_out, int sync);
+
+/* `batch` transforms of the same kind in one launch sequence (e.g. the 13 coset FFTs of
+ * quotient_poly.rs:72-120); vector b starts at d_in + b*in_stride / d_out + b*out_stride elements */
+int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, size_t in_stride,
+                      void* d_out, size_t out_stride, size_t batch, int sync);
+
+/* ---- device memory helpers for host layers that keep polynomials resident -------------- */
+int apb_dev_alloc(size_t bytes, void** d_ptr);
+int apb_dev_free(void* d_ptr);
+int apb_dev_upload(void* d_dst, const void* h_src, size_t bytes);
+int apb_dev_download(void* h_dst, const void* d_src, size_t bytes);
+int apb_dev_sync(void);
+void* apb_stream(void);                     /* the cudaStream_t all work is enqueued on */
+
+/* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
+/* element-wise field op on the device: op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont.
+ * field: 0 Fr381, 1 Fq381, 2 Fr377, 3 Fq377.  a, b, out: count x (4 or 6) u64. */
+int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+uint64_t apb_kernel_launches(void);
+/* timed microbenchmark of dependent IMAD.WIDE chains: returns multiply-adds per second */
+int apb_imad_peak(double* wide_imad_per_s, double* imad32_per_s);
+/* milliseconds of device time of the last blocking apb_msm / apb_ntt call (CUDA events) */
+double apb_last_device_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APB_H */
