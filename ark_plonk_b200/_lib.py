@@ -68,6 +68,10 @@ class Lib:
         c.apb_kernel_launches.restype = C.c_uint64
         c.apb_imad_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
         c.apb_last_device_ms.restype = C.c_double
+        c.apb_set_profiling.argtypes = [ci]
+        c.apb_set_profiling.restype = None
+        c.apb_msm_phase_ms.argtypes = [C.POINTER(C.c_double)]
+        c.apb_msm_phase_ms.restype = None
 
     # ------------------------------------------------------------------
     def check(self, rc: int):
@@ -85,6 +89,14 @@ class Lib:
 
     def last_device_ms(self) -> float:
         return float(self.c.apb_last_device_ms())
+
+    def set_profiling(self, on: bool):
+        self.c.apb_set_profiling(1 if on else 0)
+
+    def msm_phase_ms(self):
+        arr = (C.c_double * 4)()
+        self.c.apb_msm_phase_ms(arr)
+        return dict(zip(("sort", "accumulate", "stitch", "reduce"), list(arr)))
 
     def imad_peak(self):
         w, n = C.c_double(), C.c_double()

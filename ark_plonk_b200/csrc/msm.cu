@@ -32,6 +32,8 @@
 namespace apb {
 
 int g_num_sms = 1;
+int g_profile = 0;
+double g_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sort, accumulate, stitch, trees, copy+host epilogue
 
 static const int MAX_BATCH = 16;
 #ifdef APB_EMU
@@ -552,6 +554,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         ck->h_out_cap = out_bytes;
     }
 
+    cudaEvent_t ev[6];
+    if (g_profile) { for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], g_stream); }
     // 1. histogram  2. scan  3. scatter
     APB_CUDA_TRY(cudaMemsetAsync(ck->counts, 0, (size_t)(nbuckets + 1) * 4 * 3, g_stream));
     APB_CUDA_TRY(cudaMemsetAsync(ck->bucket_sums, 0, (size_t)nbuckets * 192, g_stream));
@@ -561,17 +565,29 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     APB_KLAUNCH(k_hist, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
     APB_KLAUNCH(k_scan_exclusive, 1, SCAN_THREADS, 0, (const uint32_t*)ck->counts, ck->offsets, nbuckets);
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
+    if (g_profile) cudaEventRecord(ev[1], g_stream);
     // 4. accumulate  5. stitch
     APB_KLAUNCH(k_msm_accumulate<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                 (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    if (g_profile) cudaEventRecord(ev[2], g_stream);
     APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
                 (const void*)ck->partials, (const int32_t*)ck->part_bucket);
+    if (g_profile) cudaEventRecord(ev[3], g_stream);
     // 6. bucket reduction trees
     APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_a, 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs);
     APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_b, 128, 0, (const void*)ck->stage_a, ck->stage_b, (const TreeJob*)(ck->jobs + njobs_a));
     APB_CHECK_LAUNCH();
+    if (g_profile) cudaEventRecord(ev[4], g_stream);
     APB_CUDA_TRY(cudaMemcpyAsync(ck->h_out, ck->stage_b, out_bytes, cudaMemcpyDeviceToHost, g_stream));
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    if (g_profile) {
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            g_phase_ms[i] = ms;
+        }
+        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+    }
 
     // 7. host epilogue: Horner over weight bits, fold windows, normalise
     const host::Pt* V = reinterpret_cast<const host::Pt*>(ck->h_out);
@@ -684,6 +700,11 @@ extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, c
         if (rc != APB_OK) return rc;
     }
     return APB_OK;
+}
+
+extern "C" void apb_set_profiling(int on) { g_profile = on; }
+extern "C" void apb_msm_phase_ms(double out[4]) {
+    for (int i = 0; i < 4; i++) out[i] = g_phase_ms[i];
 }
 
 extern "C" int apb_g1_compress(int curve, const uint64_t xyz[18], uint8_t out[48]) {

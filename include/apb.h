@@ -128,6 +128,10 @@ int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
 uint64_t apb_kernel_launches(void);
 /* timed microbenchmark of dependent IMAD.WIDE chains: returns multiply-adds per second */
 int apb_imad_peak(double* wide_imad_per_s, double* imad32_per_s);
+/* per-phase CUDA-event timing of the last MSM: [sort, accumulate, stitch, reduce trees] in ms
+ * (recorded only after apb_set_profiling(1)) */
+void apb_set_profiling(int on);
+void apb_msm_phase_ms(double out[4]);
 /* milliseconds of device time of the last blocking apb_msm / apb_ntt call (CUDA events) */
 double apb_last_device_ms(void);
 
