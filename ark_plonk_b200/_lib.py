@@ -68,6 +68,7 @@ class Lib:
         c.apb_kernel_launches.restype = C.c_uint64
         c.apb_imad_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
         c.apb_last_device_ms.restype = C.c_double
+        c.apb_mul_bench.argtypes = [ci, ci, ci, ci, C.c_uint32, C.POINTER(C.c_double)]
         c.apb_set_profiling.argtypes = [ci]
         c.apb_set_profiling.restype = None
         c.apb_msm_phase_ms.argtypes = [C.POINTER(C.c_double)]
@@ -97,6 +98,11 @@ class Lib:
         arr = (C.c_double * 4)()
         self.c.apb_msm_phase_ms(arr)
         return dict(zip(("sort", "accumulate", "stitch", "reduce"), list(arr)))
+
+    def mul_bench(self, field, threads, blocks_per_sm, ilp, iters=2000):
+        v = C.c_double()
+        self.check(self.c.apb_mul_bench(field, threads, blocks_per_sm, ilp, iters, C.byref(v)))
+        return v.value
 
     def imad_peak(self):
         w, n = C.c_double(), C.c_double()

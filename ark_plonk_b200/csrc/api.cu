@@ -80,9 +80,68 @@ __global__ void __launch_bounds__(256) k_imad_bench(uint32_t* out, uint32_t iter
 #endif
 }
 
+// dependent Montgomery products: ILP independent chains of x <- x * y per thread
+template <class P, int ILP>
+__global__ void k_mul_bench(void* out, uint32_t iters) {
+    Fp<P> x[ILP], y = Fp<P>::r2();
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        x[k] = Fp<P>::one();
+        x[k].v[0] += threadIdx.x + k;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = x[k] * y;
+    }
+    Fp<P> s = x[0];
+#pragma unroll
+    for (int k = 1; k < ILP; k++) s = s + x[k];
+    if (s.v[0] == 0x12345 && s.v[1] == 77) store_fp<P>(out, 0, s);
+}
+
 }  // namespace apb
 
 using namespace apb;
+
+template <class P>
+static int run_mul_bench(int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
+    void* d_out = nullptr;
+    APB_CUDA_TRY(cudaMalloc(&d_out, 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    unsigned blocks = (unsigned)(g_num_sms * blocks_per_sm);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, g_stream);
+        auto k1 = k_mul_bench<P, 1>;
+        auto k2 = k_mul_bench<P, 2>;
+        auto k4 = k_mul_bench<P, 4>;
+        if (ilp == 1) APB_KLAUNCH(k1, blocks, threads, 0, d_out, iters);
+        else if (ilp == 2) APB_KLAUNCH(k2, blocks, threads, 0, d_out, iters);
+        else APB_KLAUNCH(k4, blocks, threads, 0, d_out, iters);
+        cudaEventRecord(e1, g_stream);
+        APB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    int eff_ilp = ilp == 1 ? 1 : (ilp == 2 ? 2 : 4);
+    *muls_per_s = (double)blocks * threads * iters * eff_ilp / (best * 1e-3);
+    return APB_OK;
+}
+
+extern "C" int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
+    APB_REQUIRE_INIT();
+    if (!muls_per_s) return set_err(APB_ERR_INVALID_ARG, "apb_mul_bench: null out");
+    switch (field) {
+        case 0: return run_mul_bench<Fr381>(threads, blocks_per_sm, ilp, iters, muls_per_s);
+        case 1: return run_mul_bench<Fq381>(threads, blocks_per_sm, ilp, iters, muls_per_s);
+        case 2: return run_mul_bench<Fr377>(threads, blocks_per_sm, ilp, iters, muls_per_s);
+        default: return run_mul_bench<Fq377>(threads, blocks_per_sm, ilp, iters, muls_per_s);
+    }
+}
 
 extern "C" int apb_init(int device) {
     if (g_inited) return APB_OK;

@@ -186,11 +186,12 @@ APB_D void store_xyzz(void* arr, uint64_t idx, const XYZZ<FQ>& p) {
     store_fp<FQ>(arr, 4 * idx + 3, p.zzz);
 }
 
-// Each thread owns entries [t*E, (t+1)*E) of the bucket-sorted list.
-template <class FQ>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
-                                                        const void* bases, uint32_t E, void* bucket_sums, void* partials,
-                                                        int32_t* part_bucket) {
+// Each thread owns entries [t*E, (t+1)*E) of the bucket-sorted list.  The next point is
+// fetched (entry id, then the 96-byte affine record) while the current mixed add runs.
+template <class FQ, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
+                                                              const void* bases, uint32_t E, void* bucket_sums, void* partials,
+                                                              int32_t* part_bucket) {
     typedef Fp<FQ> F;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t M = offsets[nbuckets];
@@ -207,17 +208,27 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* entries,
     }
     uint32_t b = lo;
     while (offsets[b + 1] <= pos) b++;     // skip empty buckets sharing the same offset
+    uint32_t e_cur = entries[pos];
+    F px, py;
+    load_affine<FQ>(bases, e_cur & 0x7fffffffu, px, py);
     while (pos < end) {
         const uint64_t bstart = offsets[b], bend = offsets[b + 1];
         const uint64_t run_start = pos, run_end = bend < end ? bend : end;
         XYZZ<FQ> acc = XYZZ<FQ>::identity();
-        for (; pos < run_end; pos++) {
-            uint32_t e = entries[pos];
-            F px, py;
-            load_affine<FQ>(bases, e & 0x7fffffffu, px, py);
-            if (px.is_zero() && py.is_zero()) continue;          // point at infinity
-            if (e >> 31) py = py.neg();
-            acc.add_affine(px, py);
+        while (pos < run_end) {
+            uint32_t e_nxt = 0;
+            F nx, ny;
+            const bool more = pos + 1 < end;
+            if (more) {
+                e_nxt = entries[pos + 1];
+                load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
+            }
+            if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
+                if (e_cur >> 31) py = py.neg();
+                acc.add_affine(px, py);
+            }
+            pos++;
+            if (more) { e_cur = e_nxt; px = nx; py = ny; }
         }
         const bool head = run_start == bstart, tail = run_end == bend;
         if (head && tail) {
@@ -499,8 +510,18 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     const uint64_t Mmax = (uint64_t)total * g.W;
     if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
 
-    // chunk size for the accumulate pass
-    uint64_t target_threads = (uint64_t)g_num_sms * 384;
+    // chunk size for the accumulate pass: exactly one resident wave of threads
+    static int acc_variant = -1, resident_blocks[2] = {2, 3};
+    if (acc_variant < 0) {
+        acc_variant = 0;
+        if (const char* e = getenv("APB_MSM_ACC_VARIANT")) acc_variant = atoi(e) ? 1 : 0;
+#ifndef APB_EMU
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 3>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
+#endif
+    }
+    uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[acc_variant] * 128;
     uint32_t E = (uint32_t)((Mmax + target_threads - 1) / target_threads);
     if (E < 8) E = 8;
     if (const char* e = getenv("APB_MSM_CHUNK")) E = (uint32_t)atoi(e);
@@ -567,8 +588,14 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
     if (g_profile) cudaEventRecord(ev[1], g_stream);
     // 4. accumulate  5. stitch
-    APB_KLAUNCH(k_msm_accumulate<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
-                (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    auto k_acc2 = k_msm_accumulate<FQ, 2>;
+    auto k_acc3 = k_msm_accumulate<FQ, 3>;
+    if (acc_variant == 0)
+        APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    else
+        APB_KLAUNCH(k_acc3, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[2], g_stream);
     APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
                 (const void*)ck->partials, (const int32_t*)ck->part_bucket);

@@ -128,6 +128,8 @@ int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
 uint64_t apb_kernel_launches(void);
 /* timed microbenchmark of dependent IMAD.WIDE chains: returns multiply-adds per second */
 int apb_imad_peak(double* wide_imad_per_s, double* imad32_per_s);
+/* throughput of dependent Montgomery products (ilp independent chains per thread) at a given occupancy */
+int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s);
 /* per-phase CUDA-event timing of the last MSM: [sort, accumulate, stitch, reduce trees] in ms
  * (recorded only after apb_set_profiling(1)) */
 void apb_set_profiling(int on);
