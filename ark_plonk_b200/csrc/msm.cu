@@ -208,42 +208,49 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* en
     }
     uint32_t b = lo;
     while (offsets[b + 1] <= pos) b++;     // skip empty buckets sharing the same offset
+    // One flat loop over the chunk: every lane performs its mixed add in the same iteration
+    // (bucket borders fall at different positions in different lanes; a nested run loop lets
+    // the lanes drift apart and the warp then executes the add twice at half occupancy).
     uint32_t e_cur = entries[pos];
     F px, py;
     load_affine<FQ>(bases, e_cur & 0x7fffffffu, px, py);
+    uint64_t bstart = offsets[b], bend = offsets[b + 1], run_start = pos;
+    XYZZ<FQ> acc = XYZZ<FQ>::identity();
     while (pos < end) {
-        const uint64_t bstart = offsets[b], bend = offsets[b + 1];
-        const uint64_t run_start = pos, run_end = bend < end ? bend : end;
-        XYZZ<FQ> acc = XYZZ<FQ>::identity();
-        while (pos < run_end) {
-            uint32_t e_nxt = 0;
-            F nx, ny;
-            const bool more = pos + 1 < end;
-            if (more) {
-                e_nxt = entries[pos + 1];
-                load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
+        uint32_t e_nxt = 0;
+        F nx, ny;
+        const bool more = pos + 1 < end;
+        if (more) {
+            e_nxt = entries[pos + 1];
+            load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
+        }
+        if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
+            if (e_cur >> 31) py = py.neg();
+            acc.add_affine(px, py);
+        }
+        pos++;
+        if (pos == bend || pos == end) {                     // run finished: flush
+            const bool head = run_start == bstart, tail = pos == bend;
+            if (head && tail) {
+                store_xyzz<FQ>(bucket_sums, b, acc);
+            } else if (head) {          // bucket continues in the next chunk(s)
+                store_xyzz<FQ>(partials, 2 * t + 1, acc);
+                part_bucket[2 * t + 1] = (int32_t)b;
+            } else {                    // bucket began in an earlier chunk
+                store_xyzz<FQ>(partials, 2 * t, acc);
+                part_bucket[2 * t] = (int32_t)b;
             }
-            if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
-                if (e_cur >> 31) py = py.neg();
-                acc.add_affine(px, py);
+            if (pos < end) {
+                b++;
+                while (offsets[b + 1] <= pos) b++;
+                bstart = offsets[b];
+                bend = offsets[b + 1];
+                run_start = pos;
+                acc = XYZZ<FQ>::identity();
             }
-            pos++;
-            if (more) { e_cur = e_nxt; px = nx; py = ny; }
         }
-        const bool head = run_start == bstart, tail = run_end == bend;
-        if (head && tail) {
-            store_xyzz<FQ>(bucket_sums, b, acc);
-        } else if (head) {          // bucket continues in the next chunk(s)
-            store_xyzz<FQ>(partials, 2 * t + 1, acc);
-            part_bucket[2 * t + 1] = (int32_t)b;
-        } else {                    // bucket began in an earlier chunk
-            store_xyzz<FQ>(partials, 2 * t, acc);
-            part_bucket[2 * t] = (int32_t)b;
-        }
-        if (pos < end) {
-            b++;
-            while (offsets[b + 1] <= pos) b++;
-        }
+        __syncwarp();
+        if (more) { e_cur = e_nxt; px = nx; py = ny; }
     }
 }
 

@@ -24,6 +24,7 @@
 
 namespace apb {
 
+extern int g_num_sms;
 static const int COSET_LO_BITS = 10;
 
 struct NttPassArgs {
@@ -316,9 +317,11 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
         A.out_batch_stride = last ? out_stride : d->n;
         A.roots = inverse ? d->itw : d->tw;
         A.in_len = first ? in_len : ~(uint64_t)0;
-        // columns: keep T*C <= 4096 elements (128 KB of shared memory)
-        uint32_t lc = 12 > lt ? 12 - lt : 0;
+        // columns: keep T*C <= 2048 elements (64 KB of shared memory -> >= 2 CTAs per SM) and
+        // enough tiles to fill the chip a few times over
+        uint32_t lc = 11 > lt ? 11 - lt : 0;
         if ((int)lc > log_cols_max) lc = log_cols_max;
+        while (lc > 0 && ((d->n >> (lt + lc)) * batch) < (uint64_t)4 * g_num_sms) lc--;
         if (!last) {
             if (lc > sbits) lc = sbits;
             A.log_c = lc;
