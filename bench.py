@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200 proving hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msm|ntt] [--log-n L]
+    python bench.py --impl reference ...      # the CPU arm (arkworks-algorithm restatement)
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  msm : one KZG10 commitment MSM over 2^L (default 2^18) BLS12-381 G1 points per GPU
+        (resident powers + precomputed table in HBM, seeded uniform scalars)
+  ntt : one coset FFT of 2^L (default 2^20) Fr elements per GPU
+`value` is device-resident throughput (inputs in HBM when the timed region starts); `e2e` is
+the same metric through the blocking C-ABI call with HOST buffers (pinned scalars in, result
+out).  With --gpus N (torchrun, one rank per GPU) every rank owns a shard of N*2^L points; the
+partial sums (144 B each) are exchanged with one NCCL all-gather per step: weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MSM_IMAD_PER_POINT = 48_000          # 16 windows x 10 Fq-mul x 300 wide multiply-adds
+FR_MUL_IMAD = 136
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])
+    ap.add_argument("--log-n", type=int, default=0)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons during the timed region (NVML)"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------
+def cpu_msm_baseline(log_sample: int, threads: int, seed: bytes):
+    """arkworks-algorithm restatement (oracle/c) on host cores over a bounded sample."""
+    from ark_plonk_b200 import encoding as enc
+    from ark_plonk_b200 import synth
+    from oracle import cbuild
+    n = 1 << log_sample
+    pts = synth.progression_bases(0, 12345, 67891, n)
+    B = enc.g1_affine_to_mont(0, pts)
+    S = synth.seeded_scalars(0, n, seed=seed)
+    t0 = time.perf_counter()
+    out = cbuild.msm(0, B, S, threads=threads)
+    dt = time.perf_counter() - t0
+    exp = synth.progression_expected(0, 12345, 67891, synth.limbs_to_int_list(S))
+    assert out is not None and tuple(enc.fq_from_mont(0, out.reshape(2, 6))) == exp
+    return n / dt / 1e6, dt
+
+
+def cpu_ntt_baseline(log_n: int, threads: int):
+    from oracle import cbuild
+    rng = np.random.default_rng(7)
+    X = rng.integers(0, 1 << 62, size=(1 << log_n, 4), dtype=np.uint64)
+    t0 = time.perf_counter()
+    cbuild.ntt(0, 2, X, log_n, threads=threads)
+    dt = time.perf_counter() - t0
+    return 2 * (1 << log_n) * 32 / dt / 1e9, dt
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm (C restatement; the Rust reference cannot
+    be built in this image) with all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cbuild
+    cbuild.build()
+    cores = host_cores()
+    vals, times = [], []
+    if args.workload == "msm":
+        log_n = args.log_n or 18
+        log_sample = min(log_n, 15)
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_msm_baseline(log_sample, cores, b"ref%d" % i)
+            if i >= args.warmup:
+                vals.append(v)
+                times.append(dt)
+        metric, unit = "msm_mpts_per_s", "Mpts/s"
+        workload = "KZG10 commitment MSM, BLS12-381 G1, 2^%d points per GPU" % log_n
+        sample = "VariableBaseMSM over 2^%d of the 2^%d points per step" % (log_sample, log_n)
+    else:
+        log_n = args.log_n or 20
+        log_sample = min(log_n, 18)
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_ntt_baseline(log_sample, cores)
+            if i >= args.warmup:
+                vals.append(v)
+                times.append(dt)
+        metric, unit = "ntt_gb_per_s", "GB/s"
+        workload = "coset FFT, BLS12-381 Fr, 2^%d elements per GPU" % log_n
+        sample = "coset_fft of 2^%d elements per step" % log_sample
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb integers", "data": "synthetic",
+        "config": {"workload": workload, "curve": "BLS12-381"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "arkworks-0.3-algorithm restatement in C (oracle/c); the Rust reference cannot be built here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from ark_plonk_b200 import encoding as enc
+    from ark_plonk_b200 import kzg, synth
+    from ark_plonk_b200._lib import get_lib
+    from ark_plonk_b200.domain import Radix2EvaluationDomain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = get_lib()
+    lib.init(local)
+    stream = torch.cuda.ExternalStream(lib.c.apb_stream())
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wide_peak, _ = lib.imad_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    line = {}
+    if args.workload == "msm":
+        log_n = args.log_n or 18
+        n = 1 << log_n
+        # rank r owns points [r*n, (r+1)*n) of a (world*n)-point MSM: P_i = [a + i b]G
+        a, b = 12345, 67891
+        pts = synth.progression_bases(0, a + rank * n * b, b, n)
+        ck = kzg.CommitterKey(0, enc.g1_affine_to_mont(0, pts))
+        S = synth.seeded_scalars(0, n, seed=b"bench%d" % rank)
+        dS = torch.from_numpy(S.view(np.int64)).cuda()
+        S_pinned = torch.from_numpy(S.view(np.int64)).pin_memory()
+        out = np.zeros(18, dtype=np.uint64)
+        gathered = torch.zeros((world, 18), dtype=torch.int64, device="cuda") if world > 1 else None
+
+        def step_dev():
+            lib.check(lib.c.apb_msm_dev(ck._h, 0, dS.data_ptr(), n, 0, out.ctypes.data))
+            if world > 1:       # exchange the 144-byte partial sums; every rank folds them
+                mine = torch.from_numpy(out.view(np.int64)).cuda()
+                dist.all_gather_into_tensor(gathered, mine)
+
+        def step_e2e():
+            lib.check(lib.c.apb_msm(ck._h, 0, S_pinned.data_ptr(), n, 0, out.ctypes.data))
+            if world > 1:
+                mine = torch.from_numpy(out.view(np.int64)).cuda()
+                dist.all_gather_into_tensor(gathered, mine)
+
+        lib.set_profiling(True)
+        for _ in range(W):
+            step_dev()
+        # correctness of this rank's partial sum (closed form), outside the timed region
+        exp = synth.progression_expected(0, a + rank * n * b, b, synth.limbs_to_int_list(S))
+        assert enc.g1_from_xyz(0, out) == exp, "MSM result mismatch"
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = lib.kernel_launches()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc_ms = []
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(K):
+            step_dev()
+            acc_ms.append(lib.msm_phase_ms()["accumulate"])
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.kernel_launches() - launches0
+        clocks = sampler.result()
+        ms_per_step = total_ms / K
+        value = world * n / (ms_per_step * 1e-3) / 1e6
+        # end to end through the blocking C-ABI call with host scalars
+        for _ in range(W):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+        acc = float(np.mean(acc_ms))
+        achieved = n * MSM_IMAD_PER_POINT / (acc * 1e-3) / 1e12
+        line = {
+            "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "ms_per_step": ms_per_step,
+            "config": {"workload": "KZG10 commitment MSM, BLS12-381 G1, 2^%d points per GPU" % log_n,
+                       "curve": "BLS12-381", "points_per_gpu": n, "digit_bits": 16, "precomputed_copies": 16,
+                       "l2": "inputs exceed L2 (resident base table %d MB)" % (n * 16 * 96 >> 20)},
+            "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32,
+                    "d2h_bytes_per_step": 144 + 15 * 192},
+            "roofline": {"kernel": "k_msm_accumulate", "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
+                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": None,
+                         "kernel_ms": acc, "kernel_share_of_step": acc / ms_per_step,
+                         "peak_source": "measured live: independent mad.wide.u32 chains (apb_imad_peak)",
+                         "note": "algorithmic 48000 wide multiply-adds per point (SURVEY 8d); carry-chained "
+                                 "IMAD.WIDE.X issues at half the plain IMAD.WIDE rate, so 0.5 is this instruction mix's ceiling"},
+        }
+        if rank == 0 and world == 1:
+            v, dt = cpu_msm_baseline(min(log_n, 15), host_cores(), b"cpu")
+            line["cpu_baseline"] = {"value": v, "unit": "Mpts/s", "cores": host_cores(), "kind": "port",
+                                    "sample": "arkworks-algorithm VariableBaseMSM (oracle/c) over 2^%d points, %.1f s" % (min(log_n, 15), dt)}
+    else:
+        log_n = args.log_n or 20
+        n = 1 << log_n
+        dom = Radix2EvaluationDomain(0, n)
+        x = torch.randint(0, 2 ** 62, (n, 4), dtype=torch.int64, device="cuda")
+        y = torch.empty_like(x)
+        hx = x.cpu().pin_memory()
+        hy = np.empty((n, 4), dtype=np.uint64)
+
+        def step_dev():
+            dom.ntt_dev(2, x.data_ptr(), n, y.data_ptr())
+
+        def step_e2e():
+            lib.check(lib.c.apb_ntt(dom._h, 2, hx.data_ptr(), n, hy.ctypes.data))
+
+        for _ in range(W):
+            step_dev()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = lib.kernel_launches()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            for _ in range(K):
+                step_dev()
+            e1.record()
+        barrier()
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.kernel_launches() - launches0
+        clocks = sampler.result()
+        ms_per_step = total_ms / K
+        gbs = 2 * n * 32 / (ms_per_step * 1e-3) / 1e9
+        for _ in range(W):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+        imad = (n / 2 * log_n + n) * FR_MUL_IMAD / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": "ntt_gb_per_s", "value": world * gbs, "unit": "GB/s", "ms_per_step": ms_per_step,
+            "config": {"workload": "coset FFT, BLS12-381 Fr, 2^%d elements per GPU" % log_n, "curve": "BLS12-381",
+                       "l2": "vector %d MB %s L2" % (n * 32 >> 20, "exceeds" if n * 32 > 126 << 20 else "fits in")},
+            "e2e": {"value": world * 2 * n * 32 / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n * 32,
+                    "d2h_bytes_per_step": n * 32},
+            "roofline": {"kernel": "k_ntt_pass", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "int32": {"achieved": imad, "peak": wide_peak / 1e12, "unit": "T wide-IMAD/s", "frac": imad / (wide_peak / 1e12)},
+                         "note": "2*N*32 algorithmic bytes; the transform is INT32-issue bound (SURVEY 8d), both fractions reported"},
+        }
+        if rank == 0 and world == 1:
+            v, dt = cpu_ntt_baseline(min(log_n, 18), host_cores())
+            line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": host_cores(), "kind": "port",
+                                    "sample": "arkworks-algorithm coset_fft (oracle/c) of 2^%d elements, %.2f s" % (min(log_n, 18), dt)}
+
+    line.update({"n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                 "dtype": "u32-limb integers (381/255-bit Montgomery)", "data": "synthetic", "gpu_launches": int(launches),
+                 "clocks": clocks})
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
