@@ -44,6 +44,8 @@ class Lib:
         c.apb_last_error.restype = C.c_char_p
         c.apb_version.restype = C.c_char_p
         c.apb_ck_upload.argtypes = [ci, vp, sz, C.POINTER(vp)]
+        c.apb_ck_from_tau.argtypes = [ci, vp, vp, sz, C.POINTER(vp)]
+        c.apb_ck_download.argtypes = [vp, sz, sz, vp]
         c.apb_ck_size.argtypes = [vp, C.POINTER(sz)]
         c.apb_ck_free.argtypes = [vp]
         c.apb_ck_free.restype = None
@@ -68,6 +70,21 @@ class Lib:
         c.apb_kernel_launches.restype = C.c_uint64
         c.apb_imad_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
         c.apb_last_device_ms.restype = C.c_double
+        vpp, szp = C.POINTER(vp), C.POINTER(sz)
+        c.apb_fr_lincomb.argtypes = [ci, sz, vpp, szp, vp, vp, sz]
+        c.apb_plonk_lookup_f.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, sz]
+        c.apb_plonk_combine_split.argtypes = [ci, vp, vp, sz, vp, vp]
+        c.apb_plonk_perm_z.argtypes = [vp, vpp, vpp, vp, vp, vp]
+        c.apb_plonk_lookup_z2.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+        c.apb_plonk_quotient.argtypes = [ci, vpp, vp, vp, vp, sz]
+        c.apb_poly_eval.argtypes = [ci, sz, vpp, szp, vp, vp]
+        c.apb_poly_divide_linear.argtypes = [ci, vp, sz, vp, vp]
+        c.apb_transcript_new.argtypes = [C.c_char_p, sz, vpp]
+        c.apb_transcript_append.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
+        c.apb_transcript_challenge.argtypes = [vp, C.c_char_p, sz, vp, sz]
+        c.apb_transcript_free.argtypes = [vp]
+        c.apb_transcript_free.restype = None
+        c.apb_dev_sync.argtypes = []
         c.apb_mul_bench.argtypes = [ci, ci, ci, ci, C.c_uint32, C.POINTER(C.c_double)]
         c.apb_set_profiling.argtypes = [ci]
         c.apb_set_profiling.restype = None

@@ -364,6 +364,43 @@ __global__ void __launch_bounds__(128) k_ck_precompute(void* bases, uint64_t n, 
     }
 }
 
+// bases[i] = [tau^i] G as affine points: powers[i] holds tau^i (Fr, Montgomery)
+template <class CV>
+__global__ void __launch_bounds__(128) k_srs_powers(void* bases, const void* powers, uint64_t n, const void* gen_xy) {
+    typedef typename CV::FQ FQ;
+    typedef typename CV::FR FR;
+    typedef Fp<FQ> Fe;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<FR> s = load_fp<FR>(powers, i).from_mont();
+    Fe gx = load_fp<FQ>(gen_xy, 0), gy = load_fp<FQ>(gen_xy, 1);
+    XYZZ<FQ> acc = XYZZ<FQ>::identity();
+    for (int bit = FR::BITS - 1; bit >= 0; bit--) {
+        acc = acc.dbl();
+        if ((s.v[bit >> 5] >> (bit & 31)) & 1) acc.add_affine(gx, gy);
+    }
+    Fe ax = Fe::zero(), ay = Fe::zero();
+    if (!acc.is_identity()) {
+        Fe zinv = fp_inverse<FQ>(acc.zzz);
+        Fe r = acc.zz * zinv;
+        ax = acc.x * r.sqr();
+        ay = acc.y * zinv;
+    }
+    store_fp<FQ>(bases, 2 * i, ax);
+    store_fp<FQ>(bases, 2 * i + 1, ay);
+}
+template <class FR>
+__global__ void k_tau_powers(void* out, uint64_t count, const void* pow2) {
+    typedef Fp<FR> F;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    F acc = F::one();
+    uint64_t e = i;
+    for (int k = 0; e != 0; k++, e >>= 1)
+        if (e & 1) acc = acc * load_fp<FR>(pow2, k);
+    store_fp<FR>(out, i, acc);
+}
+
 }  // namespace apb
 
 using namespace apb;
@@ -404,17 +441,12 @@ static int grow(T** p, size_t* cap, size_t need_bytes) {
     return APB_OK;
 }
 
-extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out) {
-    if (!out || (!xy && n)) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: null argument");
-    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: bad curve %d", curve);
-    APB_REQUIRE_INIT();
+static int ck_alloc(int curve, size_t n, apb_ck_s** out) {
     apb_ck_s* ck = new apb_ck_s();
     memset(ck, 0, sizeof(*ck));
     ck->magic = CK_MAGIC;
     ck->curve = curve;
     ck->n = n;
-    // precompute geometry: 16-bit steps -> 16 copies (all digit positions share one bucket set);
-    // very large keys use 64-bit steps (4 copies, 4 effective windows) to bound memory.
     size_t big = (size_t)1 << 24;
     if (const char* e = getenv("APB_MSM_FULL_PRECOMP_MAX")) big = (size_t)atoll(e);
     if (n <= big) { ck->step = 16; ck->F = 16; } else { ck->step = 64; ck->F = 4; }
@@ -425,14 +457,77 @@ extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* 
     }
     size_t bytes = (n ? n : 1) * ck->F * 96;
     cudaError_t e = cudaMalloc(&ck->bases, bytes);
-    if (e != cudaSuccess) { delete ck; return set_err(APB_ERR_OOM, "apb_ck_upload: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { delete ck; return set_err(APB_ERR_OOM, "commitment key: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    *out = ck;
+    return APB_OK;
+}
+static int ck_precompute(apb_ck_s* ck) {
+    if (!ck->n) return APB_OK;
+    unsigned blocks = (unsigned)((ck->n + 127) / 128);
+    if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
+    else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
+    APB_CHECK_LAUNCH();
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+
+// KZG10 setup with a caller-supplied tau: powers_of_g[i] = [tau^i] G computed on the device and
+// kept resident (the reference samples tau from OsRng: benches/plonk.rs:98, PC::setup).
+// generator_xy: 12 u64 affine generator (Montgomery); tau: 4 u64 Montgomery.
+extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const uint64_t* tau, size_t n, apb_ck_t* out) {
+    if (!out || !generator_xy || !tau) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: bad curve %d", curve);
+    APB_REQUIRE_INIT();
+    apb_ck_s* ck = nullptr;
+    int rc = ck_alloc(curve, n, &ck);
+    if (rc != APB_OK) return rc;
     if (n) {
-        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases, xy, n * 96, cudaMemcpyHostToDevice, g_stream));
+        host::Field f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fr381>() : host::Field::make<Fr377>();
+        uint64_t h_pow2[64 * 4], cur[4];
+        memcpy(cur, tau, 32);
+        for (int k = 0; k < 64; k++) { memcpy(h_pow2 + 4 * k, cur, 32); f.sqr(cur, cur); }
+        void *d_pow2 = nullptr, *d_powers = nullptr, *d_gen = nullptr;
+        APB_CUDA_TRY(cudaMalloc(&d_pow2, sizeof(h_pow2)));
+        APB_CUDA_TRY(cudaMalloc(&d_powers, n * 32));
+        APB_CUDA_TRY(cudaMalloc(&d_gen, 96));
+        APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2, sizeof(h_pow2), cudaMemcpyHostToDevice, g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(d_gen, generator_xy, 96, cudaMemcpyHostToDevice, g_stream));
         unsigned blocks = (unsigned)((n + 127) / 128);
-        if (curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)n, ck->F, ck->step);
-        else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)n, ck->F, ck->step);
+        if (curve == APB_CURVE_BLS12_381) {
+            APB_KLAUNCH(k_tau_powers<Fr381>, blocks, 128, 0, d_powers, (uint64_t)n, (const void*)d_pow2);
+            APB_KLAUNCH(k_srs_powers<Curve381>, blocks, 128, 0, ck->bases, (const void*)d_powers, (uint64_t)n, (const void*)d_gen);
+        } else {
+            APB_KLAUNCH(k_tau_powers<Fr377>, blocks, 128, 0, d_powers, (uint64_t)n, (const void*)d_pow2);
+            APB_KLAUNCH(k_srs_powers<Curve377>, blocks, 128, 0, ck->bases, (const void*)d_powers, (uint64_t)n, (const void*)d_gen);
+        }
         APB_CHECK_LAUNCH();
         APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+        cudaFree(d_pow2); cudaFree(d_powers); cudaFree(d_gen);
+        if ((rc = ck_precompute(ck)) != APB_OK) { apb_ck_free(ck); return rc; }
+    }
+    *out = ck;
+    return APB_OK;
+}
+
+// copies `count` resident powers starting at `first` to host memory (12 u64 each)
+extern "C" int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t* out_xy) {
+    if (!ck || ck->magic != CK_MAGIC || !out_xy) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_download: bad handle");
+    if (first + count > ck->n) return set_err(APB_ERR_INVALID_ARG, "apb_ck_download: range exceeds key size");
+    APB_CUDA_TRY(cudaMemcpyAsync(out_xy, (const char*)ck->bases + first * 96, count * 96, cudaMemcpyDeviceToHost, g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return APB_OK;
+}
+
+extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out) {
+    if (!out || (!xy && n)) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: bad curve %d", curve);
+    APB_REQUIRE_INIT();
+    apb_ck_s* ck = nullptr;
+    int rc = ck_alloc(curve, n, &ck);
+    if (rc != APB_OK) return rc;
+    if (n) {
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases, xy, n * 96, cudaMemcpyHostToDevice, g_stream));
+        if ((rc = ck_precompute(ck)) != APB_OK) { apb_ck_free(ck); return rc; }
     }
     *out = ck;
     return APB_OK;

@@ -278,6 +278,15 @@ extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
     return APB_OK;
 }
 
+// internal: lets the polynomial kernels reach the resident root table w^i, i < N/2
+extern "C" int apb_domain_info(apb_domain_t d, int* curve, uint32_t* log_n, const void** tw) {
+    if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "bad domain handle");
+    *curve = d->curve;
+    *log_n = d->log_n;
+    *tw = d->tw;
+    return APB_OK;
+}
+
 extern "C" void apb_domain_free(apb_domain_t d) {
     if (!d || d->magic != DOMAIN_MAGIC) return;
     cudaFree(d->tw); cudaFree(d->itw); cudaFree(d->clo); cudaFree(d->chi);

@@ -28,6 +28,26 @@ class CommitterKey:
         self.lib.check(self.lib.c.apb_ck_upload(curve, pts.ctypes.data_as(C.c_void_p), self.n, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_tau(cls, curve: int, tau: int, n: int, lib: Lib | None = None) -> "CommitterKey":
+        """`PC::setup` + `trim` with a known tau: [tau^i]G, i < n, generated on the device."""
+        from .synth import G1_GENERATOR
+        self = cls.__new__(cls)
+        self.lib = lib or get_lib()
+        self.curve = curve
+        self.n = n
+        gen = enc.g1_affine_to_mont(curve, [G1_GENERATOR[curve]])
+        t = enc.fr_to_mont(curve, [tau])
+        h = C.c_void_p()
+        self.lib.check(self.lib.c.apb_ck_from_tau(curve, gen.ctypes.data, t.ctypes.data, n, C.byref(h)))
+        self._h = h
+        return self
+
+    def download(self, first: int, count: int) -> np.ndarray:
+        out = np.zeros((count, 12), dtype=np.uint64)
+        self.lib.check(self.lib.c.apb_ck_download(self._h, first, count, out.ctypes.data))
+        return out
+
     @property
     def max_degree(self) -> int:
         return self.n - 1

@@ -63,6 +63,11 @@ const char* apb_version(void);
 /* xy: n packed affine points (12 u64 each, Montgomery).  Uploaded once; a table of 2^(c*k)
  * multiples may be precomputed on the device (see DESIGN.md "MSM"). */
 int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out);
+/* KZG10 setup from a caller-supplied tau (benches/plonk.rs:98 `PC::setup`, there with OsRng):
+ * powers_of_g[i] = [tau^i] G computed on the device and kept resident.  generator_xy: 12 u64,
+ * tau: 4 u64, both Montgomery. */
+int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const uint64_t* tau, size_t n, apb_ck_t* out);
+int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t* out_xy);
 int apb_ck_size(apb_ck_t ck, size_t* n);
 void apb_ck_free(apb_ck_t ck);
 
@@ -111,6 +116,45 @@ int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void*
  * quotient_poly.rs:72-120); vector b starts at d_in + b*in_stride / d_out + b*out_stride elements */
 int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, size_t in_stride,
                       void* d_out, size_t out_stride, size_t batch, int sync);
+
+/* ---- device-resident polynomial utilities and prover kernels (SURVEY.md 8f "next" rows) ----
+ * All vectors are device pointers to Fr elements (32 B, Montgomery); scalars are 4 x u64 Montgomery
+ * in host memory.  Work is enqueued on the library stream; functions that return values to the
+ * host block. */
+/* out[i] = sum_j scalars[j] * polys[j][i], i < out_len (polys zero-extended): DensePolynomial
+ * linear combinations of linearisation_poly.rs:203-349, MultiSet::compress (lookup/multiset.rs:207-213),
+ * the opening combination of sonic_pc::open */
+int apb_fr_lincomb(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* scalars,
+                   void* d_out, size_t out_len);
+/* compressed lookup query vector f (proof_system/prover.rs:252-278) */
+int apb_plonk_lookup_f(int curve, const void* q_lookup, const void* wl, const void* wr, const void* wo, const void* w4,
+                       const void* t_comp, const uint64_t* zeta, void* d_out, size_t n);
+/* MultiSet::combine_split (lookup/multiset.rs:131-174): h1, h2 of n elements each; blocking;
+ * APB_ERR_INVALID_ARG when an element of f is not in t (Error::ElementNotIndexed) */
+int apb_plonk_combine_split(int curve, const void* d_t, const void* d_f, size_t n, void* d_h1, void* d_h2);
+/* evaluations of the permutation grand product z over the domain (permutation/mod.rs:652-751, before its ifft) */
+int apb_plonk_perm_z(apb_domain_t dom, const void* const* d_wires4, const void* const* d_sigmas4, const uint64_t* beta,
+                     const uint64_t* gamma, void* d_z);
+/* evaluations of the lookup grand product z2 (permutation/mod.rs:754-822) */
+int apb_plonk_lookup_z2(apb_domain_t dom, const void* d_f, const void* d_t, const void* d_h1, const void* d_h2,
+                        const uint64_t* delta, const uint64_t* epsilon, void* d_z2);
+/* quotient evaluations on the 4n coset (quotient_poly.rs:122-173): ptrs25 = wl wr wo w4 z z2 f table h1 h2 pi(NULL ok)
+ * q_m q_l q_r q_o q_4 q_c q_arith q_lookup s1 s2 s3 s4 linear l1 ; scalars10 = alpha beta gamma delta epsilon zeta
+ * lookup_sep K1 K2 K3 ; vh_inv4 = inverses of the 4-periodic vanishing-polynomial values */
+int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* scalars10, const uint64_t* vh_inv4,
+                       void* d_out, size_t n4);
+/* k evaluations polys[j](points[j]) -> out_vals (host, Montgomery); DensePolynomial::evaluate */
+int apb_poly_eval(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* points,
+                  uint64_t* out_vals);
+/* witness polynomial p / (X - z) (len - 1 coefficients): kzg10 compute_witness_polynomial */
+int apb_poly_divide_linear(int curve, const void* d_p, size_t len, const uint64_t* z, void* d_out);
+
+/* ---- Fiat-Shamir transcript (merlin 3.0 / STROBE-128), host side: plonk-core/src/transcript.rs:16-50 */
+typedef struct apb_transcript_s* apb_transcript_t;
+int apb_transcript_new(const uint8_t* label, size_t label_len, apb_transcript_t* out);
+int apb_transcript_append(apb_transcript_t t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
+int apb_transcript_challenge(apb_transcript_t t, const uint8_t* label, size_t label_len, uint8_t* out, size_t out_len);
+void apb_transcript_free(apb_transcript_t t);
 
 /* ---- device memory helpers for host layers that keep polynomials resident -------------- */
 int apb_dev_alloc(size_t bytes, void** d_ptr);

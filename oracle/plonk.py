@@ -1,0 +1,552 @@
+"""CPU restatement of ark-plonk's prover for the benchmark circuit (TEST INFRASTRUCTURE).
+
+Oracle = test infrastructure (see oracle/__init__.py).  Restates, with Python big integers:
+  * the benchmark circuit (benches/plonk.rs:45-68; constraint_system/composer.rs:202-238,269-312,
+    493-574,580-648),
+  * circuit preprocessing (proof_system/preprocess.rs:61-88,126-243,267-452;
+    permutation/mod.rs:101-213; lookup/preprocess.rs:42-69; lookup/multiset.rs:70-79,131-174,207-213),
+  * the five-round prover (proof_system/prover.rs:163-638) with quotient_poly.rs:34-327,
+    linearisation_poly.rs:164-411, proof_system/permutation.rs:62-292, widget/arithmetic.rs:51-82,
+    widget/lookup.rs:42-203, permutation/mod.rs:652-822,
+  * the Fiat-Shamir schedule (transcript.rs:27-50) and the Proof wire
+    format (proof.rs:51-103).
+
+The reference draws 8 blinding witnesses and the SRS from OsRng (composer.rs:235, benches/plonk.rs:98);
+here tau and the 8 blinders are explicit inputs, which makes the proof a deterministic function
+(SURVEY.md section 0.5).  Range / logic / ECC gate terms are restated only for the case the
+benchmark circuit exercises (their selectors are identically zero, composer.rs:506-509,531-534, so
+the terms vanish); `assert`s enforce that.
+
+Commitments use the known tau: commit(p) = [p(tau)]G (one scalar multiplication instead of an
+MSM).  KZG open follows ark-poly-commit 0.3 sonic_pc::open (RECALLED, not vendored): p = sum
+challenge^i p_i with i from 0, witness = p / (X - z), proof = commit(witness), random_v = None.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from .curves import CURVES, Curve
+from .merlin import Transcript
+from .ntt import Domain, poly_eval
+from .serialize import ser_field, ser_g1, ser_kzg_proof, ser_string, ser_u64
+
+K1, K2, K3 = 7, 13, 17          # permutation/constants.rs:12-22
+LEFT, RIGHT, OUT, FOURTH = 0, 1, 2, 3
+
+
+# --------------------------------------------------------------------------------------------
+# constraint system (only what the benchmark circuit touches)
+# --------------------------------------------------------------------------------------------
+class Composer:
+    SELECTORS = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_4", "q_arith", "q_range", "q_logic",
+                 "q_fixed_group_add", "q_variable_group_add", "q_lookup")
+
+    def __init__(self, curve: Curve, blinders):
+        """StandardComposer::new(): zero variable + its constraint row + 3 blinding rows."""
+        assert len(blinders) == 8
+        self.curve = curve
+        self.p = curve.fr.p
+        self.n = 0
+        for s in self.SELECTORS:
+            setattr(self, s, [])
+        self.w = [[], [], [], []]                  # variable ids per wire column
+        self.variables = []                        # id -> value
+        self.variable_map = []                     # id -> [(wire, row)]
+        self.lookup_table = []                     # rows [a, b, c, d]
+        self.zero_var = self.add_input(0)
+        # constrain_to_constant(zero, 0): poly_gate(a, a, a, 0, 1, 0, 0, -0)
+        self._push_row((self.zero_var,) * 3 + (self.zero_var,), q_l=1, q_arith=1)
+        self._add_blinding_factors(blinders)
+
+    def add_input(self, value: int) -> int:
+        self.variables.append(value % self.p)
+        self.variable_map.append([])
+        return len(self.variables) - 1
+
+    def _push_row(self, wires, **sel):
+        for col, var in enumerate(wires):
+            self.w[col].append(var)
+            self.variable_map[var].append((col, self.n))
+        for s in self.SELECTORS:
+            getattr(self, s).append(sel.get(s, 0) % self.p)
+        self.n += 1
+
+    def _add_blinding_factors(self, b):
+        """composer.rs:580-648: two rows of 4 random wires, one row repeating the last pair."""
+        r1 = r2 = self.zero_var
+        for k in range(2):
+            r1 = self.add_input(b[4 * k])
+            r2 = self.add_input(b[4 * k + 1])
+            r3 = self.add_input(b[4 * k + 2])
+            r4 = self.add_input(b[4 * k + 3])
+            self._push_row((r1, r2, r3, r4))
+        self._push_row((r1, r2, self.zero_var, self.zero_var))
+
+    def add_dummy_constraints(self):
+        """composer.rs:493-548"""
+        six, one, seven, m20 = (self.add_input(6), self.add_input(1), self.add_input(7), self.add_input(-20))
+        self._push_row((six, seven, m20, one), q_m=1, q_l=2, q_r=3, q_o=4, q_c=4, q_4=1, q_arith=1, q_lookup=1)
+        self._push_row((m20, six, seven, self.zero_var), q_m=1, q_l=1, q_r=1, q_o=1, q_c=127, q_4=0, q_arith=1,
+                       q_lookup=1)
+
+    def add_dummy_lookup_table(self):
+        """composer.rs:553-574"""
+        p = self.p
+        self.lookup_table += [[6, 7, (-20) % p, 1], [(-20) % p, 6, 7, 0], [3, 1, 4, 9]]
+
+    def circuit_bound(self) -> int:
+        m = max(self.n, len(self.lookup_table))
+        return 1 << max(m - 1, 0).bit_length()
+
+    def wire_values(self, col: int):
+        return [self.variables[v] for v in self.w[col]]
+
+
+def bench_circuit(curve: Curve, degree: int, blinders) -> Composer:
+    """benches/plonk.rs:57-60 with size = 2^degree"""
+    cs = Composer(curve, blinders)
+    cs.add_dummy_lookup_table()
+    while cs.circuit_bound() < (1 << degree) - 1:
+        cs.add_dummy_constraints()
+    return cs
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+def lc(values, challenge, p):
+    """util.rs:152-171: v_0 + c v_1 + ... (Horner from the last element)"""
+    assert challenge % p not in (0, 1)
+    acc = values[-1]
+    for v in reversed(values[:-1]):
+        acc = (acc * challenge + v) % p
+    return acc
+
+
+def compress_multisets(multisets, alpha, p):
+    """MultiSet::compress (multiset.rs:207-213): element-wise lc"""
+    n = len(multisets[0])
+    assert all(len(m) == n for m in multisets)
+    return [lc([m[i] for m in multisets], alpha, p) for i in range(n)]
+
+
+def combine_split(t, f):
+    """multiset.rs:131-174: bucket by value in first-occurrence order of t, alternate halves"""
+    counters = {}
+    for e in t:
+        counters[e] = counters.get(e, 0) + 1
+    for e in f:
+        if e not in counters:
+            raise ValueError("ElementNotIndexed")
+        counters[e] += 1
+    evens, odds, parity = [], [], 0
+    for elem, count in counters.items():
+        half = count // 2
+        evens += [elem] * half
+        odds += [elem] * half
+        if count % 2 == 1:
+            if parity == 1:
+                odds.append(elem)
+                parity = 0
+            else:
+                evens.append(elem)
+                parity = 1
+    return evens, odds
+
+
+def strip(poly):
+    """DensePolynomial::from_coefficients_vec drops trailing zero coefficients"""
+    k = len(poly)
+    while k and poly[k - 1] == 0:
+        k -= 1
+    return poly[:k]
+
+
+class Kzg:
+    """SonicKZG10 with a known tau (commitments by evaluation at tau)"""
+
+    def __init__(self, curve: Curve, tau: int, max_degree: int):
+        self.curve, self.tau, self.max_degree = curve, tau % curve.fr.p, max_degree
+        self.r = curve.fr.p
+
+    def commit(self, poly):
+        poly = strip(list(poly))
+        if len(poly) > self.max_degree + 1:
+            raise ValueError("TooManyCoefficients")
+        return self.curve.mul(self.curve.G, poly_eval(self.curve.fr, poly, self.tau))
+
+    def open(self, polys, point, challenge):
+        r = self.r
+        m = max((len(q) for q in polys), default=0)
+        comb = [0] * m
+        cur = 1
+        for q in polys:
+            for i, c in enumerate(q):
+                comb[i] = (comb[i] + cur * c) % r
+            cur = cur * challenge % r
+        # witness = comb / (X - point): synthetic division, remainder dropped
+        w = [0] * max(m - 1, 0)
+        acc = 0
+        for i in range(m - 1, 0, -1):
+            acc = (comb[i] + acc * point) % r
+            w[i - 1] = acc
+        return self.commit(w), w
+
+
+# --------------------------------------------------------------------------------------------
+# preprocessing
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ProverKey:
+    n: int
+    polys: dict = field(default_factory=dict)        # selector / sigma coefficient vectors
+    evals: dict = field(default_factory=dict)        # 4n coset evaluations
+    linear_evals: list = None                        # coset_fft([0, 1]) on 4n
+    v_h_coset: list = None
+    tables: list = None                              # 4 padded table columns
+    commitments: dict = field(default_factory=dict)  # verifier-key commitments (affine points)
+
+
+def preprocess(cs: Composer, kzg: Kzg) -> ProverKey:
+    """preprocess_shared + preprocess_prover (preprocess.rs:126-243,267-423)"""
+    f, p = cs.curve.fr, cs.p
+    n = cs.circuit_bound()
+    dom = Domain.for_size(f, n)
+    dom4 = Domain.for_size(f, 4 * n)
+    pk = ProverKey(n=n)
+    # lookup table columns: pad with element 0 (multiset.rs:70-79), ifft, commit
+    cols = [[row[i] for row in cs.lookup_table] for i in range(4)]
+    pk.tables = []
+    for i, col in enumerate(cols):
+        col = list(col) if col else [0]
+        col = col + [col[0]] * (n - len(col))
+        pk.tables.append(col)
+        pk.commitments["table_%d" % (i + 1)] = kzg.commit(dom.ifft(col))
+    # pad (preprocess.rs:61-88)
+    diff = n - cs.n
+    for s in cs.SELECTORS:
+        getattr(cs, s).extend([0] * diff)
+    for col in range(4):
+        cs.w[col].extend([cs.zero_var] * diff)       # NOTE: padding rows are not added to the permutation
+    cs.n += diff
+    for s in cs.SELECTORS:
+        pk.polys[s] = strip(dom.ifft(getattr(cs, s)))
+    # sigma permutations (permutation/mod.rs:101-213)
+    sig = [[(c, i) for i in range(n)] for c in range(4)]
+    for wires in cs.variable_map:
+        for k, (col, row) in enumerate(wires):
+            sig[col][row] = wires[(k + 1) % len(wires)]
+    roots = dom.elements()
+    ks = (1, K1, K2, K3)
+    names = ("left_sigma", "right_sigma", "out_sigma", "fourth_sigma")
+    for c in range(4):
+        lagrange = [ks[col] * roots[row] % p for (col, row) in sig[c]]
+        pk.polys[names[c]] = strip(dom.ifft(lagrange))
+    for name in cs.SELECTORS + names:
+        pk.commitments[name] = kzg.commit(pk.polys[name])
+        pk.evals[name] = dom4.coset_fft(pk.polys[name])
+    pk.linear_evals = dom4.coset_fft([0, 1])
+    g_n = pow(f.generator, n, p)
+    w4 = dom4.group_gen
+    pk.v_h_coset = [(g_n * pow(w4, n * i, p) - 1) % p for i in range(4 * n)]
+    for s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
+        assert not pk.polys[s], "oracle restates range/logic/ecc gate terms only for zero selectors"
+    return pk
+
+
+# --------------------------------------------------------------------------------------------
+# prover
+# --------------------------------------------------------------------------------------------
+class PlonkTranscript:
+    """transcript.rs:16-50 over merlin"""
+
+    def __init__(self, curve: Curve, label: bytes):
+        self.t = Transcript(label)
+        self.curve = curve
+
+    def append_fr(self, label: bytes, v: int):
+        self.t.append_message(label, ser_field(self.curve.fr, v))
+
+    def append_g1(self, label: bytes, P):
+        self.t.append_message(label, ser_g1(self.curve, P))
+
+    def append_bytes(self, label: bytes, b: bytes):
+        self.t.append_message(label, b)
+
+    def challenge(self, label: bytes) -> int:
+        size = self.curve.fr.bits // 8            # size_in_bits() / 8 = 31
+        return int.from_bytes(self.t.challenge_bytes(label, size), "little") % self.curve.fr.p
+
+
+def first_lagrange_poly_scaled(dom: Domain, scale: int):
+    x = [0] * dom.size
+    x[0] = scale
+    return dom.ifft(x)
+
+
+def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark", trace: dict | None = None):
+    """Prover::prove_with_preprocessed (prover.rs:163-638).  Returns (proof dict, serialized bytes).
+
+    `trace`, if given, receives every intermediate the hot path produces (polynomials,
+    evaluation vectors, challenges) so GPU stages can be compared one by one."""
+    curve, f, p = cs.curve, cs.curve.fr, cs.p
+    n = cs.circuit_bound()
+    assert n == pk.n and cs.n <= n
+    dom = Domain.for_size(f, n)
+    dom4 = Domain.for_size(f, 4 * n)
+    tr = PlonkTranscript(curve, transcript_label)
+    T = trace if trace is not None else {}
+    tr.append_bytes(b"pi", ser_u64(0))                         # empty PublicInputs (BTreeMap) = u64 length 0
+
+    # ---- round 1: wires ------------------------------------------------------------------
+    wires = []
+    for col in range(4):
+        vals = cs.wire_values(col)
+        wires.append(vals + [0] * (n - len(vals)))
+    w_polys = [strip(dom.ifft(w)) for w in wires]
+    w_comms = [kzg.commit(q) for q in w_polys]
+    for lab, c in zip((b"w_l", b"w_r", b"w_o", b"w_4"), w_comms):
+        tr.append_g1(lab, c)
+    T.update(wires=wires, w_polys=w_polys)
+
+    # ---- round 2: lookup -----------------------------------------------------------------
+    zeta = tr.challenge(b"zeta")
+    tr.append_fr(b"zeta", zeta)
+    t_comp = compress_multisets(pk.tables, zeta, p)
+    table_poly = strip(dom.ifft(t_comp))
+    q_lookup = list(cs.q_lookup) + [0] * (n - len(cs.q_lookup))
+    fcols = [[], [], [], []]
+    for i in range(n):
+        if q_lookup[i] == 0:
+            fcols[0].append(t_comp[0])
+            for c in (1, 2, 3):
+                fcols[c].append(0)
+        else:
+            for c in range(4):
+                fcols[c].append(wires[c][i])
+    f_comp = compress_multisets(fcols, zeta, p)
+    f_poly = strip(dom.ifft(f_comp))
+    f_comm = kzg.commit(f_poly)
+    tr.append_g1(b"f", f_comm)
+    h1, h2 = combine_split(t_comp, f_comp)
+    h1_poly, h2_poly = strip(dom.ifft(h1)), strip(dom.ifft(h2))
+    h1_comm, h2_comm = kzg.commit(h1_poly), kzg.commit(h2_poly)
+    tr.append_g1(b"h1", h1_comm)
+    tr.append_g1(b"h2", h2_comm)
+    T.update(zeta=zeta, t_comp=t_comp, f_comp=f_comp, h1=h1, h2=h2, table_poly=table_poly, f_poly=f_poly,
+             h1_poly=h1_poly, h2_poly=h2_poly)
+
+    # ---- round 3: permutation ------------------------------------------------------------
+    beta = tr.challenge(b"beta"); tr.append_fr(b"beta", beta)
+    gamma = tr.challenge(b"gamma"); tr.append_fr(b"gamma", gamma)
+    delta = tr.challenge(b"delta"); tr.append_fr(b"delta", delta)
+    epsilon = tr.challenge(b"epsilon"); tr.append_fr(b"epsilon", epsilon)
+    assert len({beta, gamma, delta, epsilon}) == 4, "challenges must be different"
+    sig_names = ("left_sigma", "right_sigma", "out_sigma", "fourth_sigma")
+    sigmas = [dom.fft(pk.polys[s]) for s in sig_names]
+    roots = dom.elements()
+    ks = (1, K1, K2, K3)
+    z = [1]
+    for i in range(n - 1):
+        num = den = 1
+        for c in range(4):
+            num = num * (wires[c][i] + beta * ks[c] * roots[i] + gamma) % p
+            den = den * (wires[c][i] + beta * sigmas[c][i] + gamma) % p
+        z.append(z[-1] * num % p * pow(den, -1, p) % p)
+    z_poly = strip(dom.ifft(z))
+    z_comm = kzg.commit(z_poly)
+    tr.append_g1(b"z", z_comm)
+    # lookup permutation (permutation/mod.rs:754-822)
+    opd = (1 + delta) % p
+    eopd = epsilon * opd % p
+    z2 = [1]
+    for i in range(n - 1):
+        t_next, h1_next = t_comp[(i + 1) % n], h1[(i + 1) % n]
+        num = opd * (epsilon + f_comp[i]) % p * (eopd + t_comp[i] + delta * t_next) % p
+        den = (eopd + h1[i] + h2[i] * delta) % p * ((eopd + h2[i] + h1_next * delta) % p) % p
+        z2.append(z2[-1] * num % p * pow(den, -1, p) % p)
+    z2_poly = strip(dom.ifft(z2))
+    z2_comm = kzg.commit(z2_poly)               # NOT appended to the transcript (prover.rs:387-389)
+    pi_poly = []                                # zero public inputs
+    T.update(beta=beta, gamma=gamma, delta=delta, epsilon=epsilon, z=z, z2=z2, z_poly=z_poly, z2_poly=z2_poly)
+
+    # ---- round 4: quotient ---------------------------------------------------------------
+    alpha = tr.challenge(b"alpha"); tr.append_fr(b"alpha", alpha)
+    range_sep = tr.challenge(b"range separation challenge"); tr.append_fr(b"range seperation challenge", range_sep)
+    logic_sep = tr.challenge(b"logic separation challenge"); tr.append_fr(b"logic seperation challenge", logic_sep)
+    fixed_sep = tr.challenge(b"fixed base separation challenge"); tr.append_fr(b"fixed base separation challenge", fixed_sep)
+    var_sep = tr.challenge(b"variable base separation challenge"); tr.append_fr(b"variable base separation challenge", var_sep)
+    lookup_sep = tr.challenge(b"lookup separation challenge"); tr.append_fr(b"lookup separation challenge", lookup_sep)
+
+    N4 = 4 * n
+    l1_eval = dom4.coset_fft(first_lagrange_poly_scaled(dom, 1))
+    ev = {name: dom4.coset_fft(q) for name, q in (("z", z_poly), ("wl", w_polys[0]), ("wr", w_polys[1]),
+                                                   ("wo", w_polys[2]), ("w4", w_polys[3]), ("z2", z2_poly),
+                                                   ("f", f_poly), ("table", table_poly), ("h1", h1_poly),
+                                                   ("h2", h2_poly), ("pi", pi_poly))}
+    l1_alpha_sq = dom4.coset_fft(first_lagrange_poly_scaled(dom, alpha * alpha % p))
+    E = pk.evals
+    lsq = lookup_sep * lookup_sep % p
+    lcu = lsq * lookup_sep % p
+    quotient = []
+    for i in range(N4):
+        j = (i + 4) % N4
+        a, b, c, d = ev["wl"][i], ev["wr"][i], ev["wo"][i], ev["w4"][i]
+        # arithmetic (widget/arithmetic.rs:51-62) + public inputs
+        gate = (a * b % p * E["q_m"][i] + a * E["q_l"][i] + b * E["q_r"][i] + c * E["q_o"][i] + d * E["q_4"][i]
+                + E["q_c"][i]) % p * E["q_arith"][i] % p
+        gate = (gate + ev["pi"][i]) % p
+        # permutation (proof_system/permutation.rs:62-155)
+        x = pk.linear_evals[i]
+        zi, zn = ev["z"][i], ev["z"][j]
+        ident = (a + beta * x + gamma) % p * ((b + beta * K1 * x + gamma) % p) % p \
+            * ((c + beta * K2 * x + gamma) % p) % p * ((d + beta * K3 * x + gamma) % p) % p * zi % p * alpha % p
+        copy = (a + beta * E["left_sigma"][i] + gamma) % p * ((b + beta * E["right_sigma"][i] + gamma) % p) % p \
+            * ((c + beta * E["out_sigma"][i] + gamma) % p) % p * ((d + beta * E["fourth_sigma"][i] + gamma) % p) % p \
+            * zn % p * alpha % p
+        perm = (ident - copy + (zi - 1) * l1_alpha_sq[i]) % p
+        # lookup (widget/lookup.rs:96-151)
+        fi, ti, tn = ev["f"][i], ev["table"][i], ev["table"][j]
+        h1i, h1n, h2i = ev["h1"][i], ev["h1"][j], ev["h2"][i]
+        z2i, z2n = ev["z2"][i], ev["z2"][j]
+        la = E["q_lookup"][i] * ((lc([a, b, c, d], zeta, p) - fi) % p) % p * lookup_sep % p
+        lb = z2i * opd % p * ((epsilon + fi) % p) % p * ((eopd + ti + delta * tn) % p) % p * lsq % p
+        lcc = (-z2n) % p * ((eopd + h1i + delta * h2i) % p) % p * ((eopd + h2i + delta * h1n) % p) % p * lsq % p
+        ld = (z2i - 1) % p * l1_eval[i] % p * lcu % p
+        num = (gate + perm + la + lb + lcc + ld) % p
+        quotient.append(num * pow(pk.v_h_coset[i], -1, p) % p)
+    t_poly = strip(dom4.coset_ifft(quotient))
+    t_parts = [strip(t_poly[k * n:(k + 1) * n]) for k in range(3)] + [strip(t_poly[3 * n:])]
+    t_comms = [kzg.commit(q) for q in t_parts]
+    for lab, c in zip((b"t_1", b"t_2", b"t_3", b"t_4"), t_comms):
+        tr.append_g1(lab, c)
+    T.update(alpha=alpha, lookup_sep=lookup_sep, quotient_evals=quotient, t_poly=t_poly, evals_4n=ev)
+
+    # ---- round 5: linearisation + openings ----------------------------------------------
+    zc = tr.challenge(b"z"); tr.append_fr(b"z", zc)
+    omega = dom.group_gen
+    zw = zc * omega % p
+    P = pk.polys
+
+    def ev_at(q, x):
+        return poly_eval(f, q, x)
+
+    a_eval, b_eval, c_eval, d_eval = (ev_at(q, zc) for q in w_polys)
+    left_e, right_e, out_e = ev_at(P["left_sigma"], zc), ev_at(P["right_sigma"], zc), ev_at(P["out_sigma"], zc)
+    perm_eval = ev_at(z_poly, zw)
+    q_arith_e, q_lookup_e = ev_at(P["q_arith"], zc), ev_at(P["q_lookup"], zc)
+    q_c_e, q_l_e, q_r_e = ev_at(P["q_c"], zc), ev_at(P["q_l"], zc), ev_at(P["q_r"], zc)
+    a_next, b_next, d_next = ev_at(w_polys[0], zw), ev_at(w_polys[1], zw), ev_at(w_polys[3], zw)
+    z2_next = ev_at(z2_poly, zw)
+    h1_e, h1_next, h2_e = ev_at(h1_poly, zc), ev_at(h1_poly, zw), ev_at(h2_poly, zc)
+    f_e, table_e, table_next = ev_at(f_poly, zc), ev_at(table_poly, zc), ev_at(table_poly, zw)
+    vanishing = (pow(zc, n, p) - 1) % p
+    z_n = (vanishing + 1) % p
+    l1_z = vanishing * pow(n * (zc - 1) % p, -1, p) % p         # proof.rs:622-633
+
+    def scale(q, s):
+        return [c * s % p for c in q]
+
+    def add(*qs):
+        m = max((len(q) for q in qs), default=0)
+        out = [0] * m
+        for q in qs:
+            for i, c in enumerate(q):
+                out[i] = (out[i] + c) % p
+        return out
+
+    # arithmetic linearisation (widget/arithmetic.rs:66-82)
+    arith = scale(add(scale(P["q_m"], a_eval * b_eval % p), scale(P["q_l"], a_eval), scale(P["q_r"], b_eval),
+                      scale(P["q_o"], c_eval), scale(P["q_4"], d_eval), P["q_c"]), q_arith_e)
+    # lookup linearisation (widget/lookup.rs:154-203)
+    lk_a = scale(P["q_lookup"], (lc([a_eval, b_eval, c_eval, d_eval], zeta, p) - f_e) % p * lookup_sep % p)
+    b0 = (epsilon + f_e) % p
+    b1 = (eopd + table_e + delta * table_next) % p
+    lk_b = scale(z2_poly, (opd * b0 % p * b1 % p * lsq + l1_z * lcu) % p)
+    c0 = (-z2_next) % p * lsq % p
+    c1 = (eopd + h2_e + delta * h1_next) % p
+    lk_c = scale(h1_poly, c0 * c1 % p)
+    # permutation linearisation (proof_system/permutation.rs:156-292)
+    bz = beta * zc % p
+    pa = (a_eval + bz + gamma) % p * ((b_eval + K1 * bz + gamma) % p) % p * ((c_eval + K2 * bz + gamma) % p) % p \
+        * ((d_eval + K3 * bz + gamma) % p) % p * alpha % p
+    pb = (a_eval + beta * left_e + gamma) % p * ((b_eval + beta * right_e + gamma) % p) % p \
+        * ((c_eval + beta * out_e + gamma) % p) % p * (beta * perm_eval % p) % p * alpha % p
+    perm_lin = add(scale(z_poly, pa), scale(P["fourth_sigma"], (-pb) % p), scale(z_poly, l1_z * alpha % p * alpha % p))
+    # quotient term
+    qt = scale(t_parts[3], z_n)
+    qt = scale(add(qt, t_parts[2]), z_n)
+    qt = scale(add(qt, t_parts[1]), z_n)
+    qt = scale(add(qt, t_parts[0]), vanishing)
+    lin_poly = strip(add(arith, perm_lin, lk_a, lk_b, lk_c, scale(qt, p - 1)))
+
+    for lab, v in ((b"a_eval", a_eval), (b"b_eval", b_eval), (b"c_eval", c_eval), (b"d_eval", d_eval),
+                   (b"left_sig_eval", left_e), (b"right_sig_eval", right_e), (b"out_sig_eval", out_e),
+                   (b"perm_eval", perm_eval), (b"f_eval", f_e), (b"q_lookup_eval", q_lookup_e),
+                   (b"lookup_perm_eval", z2_next), (b"h_1_eval", h1_e), (b"h_1_next_eval", h1_next),
+                   (b"h_2_eval", h2_e)):
+        tr.append_fr(lab, v)
+    custom = [("q_arith_eval", q_arith_e), ("q_c_eval", q_c_e), ("q_l_eval", q_l_e), ("q_r_eval", q_r_e),
+              ("a_next_eval", a_next), ("b_next_eval", b_next), ("d_next_eval", d_next)]
+    for lab, v in custom:
+        tr.append_fr(lab.encode(), v)
+
+    aw_challenge = tr.challenge(b"aggregate_witness")
+    aw_polys = [lin_poly, P["left_sigma"], P["right_sigma"], P["out_sigma"], f_poly, h2_poly, table_poly] + w_polys
+    aw_open, aw_wit = kzg.open(aw_polys, zc, aw_challenge)
+    saw_challenge = tr.challenge(b"aggregate_witness")
+    saw_polys = [z_poly, w_polys[0], w_polys[1], w_polys[3], h1_poly, z2_poly, table_poly]
+    saw_open, saw_wit = kzg.open(saw_polys, zw, saw_challenge)
+    T.update(z_challenge=zc, lin_poly=lin_poly, aw_challenge=aw_challenge, saw_challenge=saw_challenge,
+             aw_witness=aw_wit, saw_witness=saw_wit)
+
+    proof = {
+        "commitments": [w_comms[0], w_comms[1], w_comms[2], w_comms[3], z_comm, f_comm, h1_comm, h2_comm, z2_comm,
+                        t_comms[0], t_comms[1], t_comms[2], t_comms[3]],
+        "aw_opening": aw_open, "saw_opening": saw_open,
+        "wire_evals": [a_eval, b_eval, c_eval, d_eval],
+        "perm_evals": [left_e, right_e, out_e, perm_eval],
+        "lookup_evals": [q_lookup_e, z2_next, h1_e, h1_next, h2_e, f_e, table_e, table_next],
+        "custom_evals": custom,
+    }
+    return proof, serialize_proof(curve, proof)
+
+
+def serialize_proof(curve: Curve, proof) -> bytes:
+    """Proof (proof.rs:51-103) in ark-serialize compressed form."""
+    out = b"".join(ser_g1(curve, c) for c in proof["commitments"])
+    out += ser_kzg_proof(curve, proof["aw_opening"]) + ser_kzg_proof(curve, proof["saw_opening"])
+    for v in proof["wire_evals"] + proof["perm_evals"] + proof["lookup_evals"]:
+        out += ser_field(curve.fr, v)
+    out += ser_u64(len(proof["custom_evals"]))
+    for lab, v in proof["custom_evals"]:
+        out += ser_string(lab) + ser_field(curve.fr, v)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# acceptance check with known tau: the KZG opening equations in discrete-log form
+# --------------------------------------------------------------------------------------------
+def check_openings(cs: Composer, pk: ProverKey, kzg: Kzg, proof, trace) -> bool:
+    """w(tau) * (tau - z) == p(tau) - p(z) for both aggregated openings, with p rebuilt from the
+    proof's commitments' pre-images (the oracle knows the polynomials) - the prover-side identity
+    PC::check would verify with pairings (proof.rs:398-425)."""
+    p = cs.p
+    f = cs.curve.fr
+    tau = kzg.tau
+    zc = trace["z_challenge"]
+    for wit, polys_key, chal, point in (
+            ("aw_witness", "aw", trace["aw_challenge"], zc),
+            ("saw_witness", "saw", trace["saw_challenge"], zc * Domain.for_size(f, pk.n).group_gen % p)):
+        polys = trace[polys_key + "_polys"] if polys_key + "_polys" in trace else None
+        if polys is None:
+            continue
+        comb_tau = comb_z = 0
+        cur = 1
+        for q in polys:
+            comb_tau = (comb_tau + cur * poly_eval(f, q, tau)) % p
+            comb_z = (comb_z + cur * poly_eval(f, q, point)) % p
+            cur = cur * chal % p
+        if poly_eval(f, trace[wit], tau) * (tau - point) % p != (comb_tau - comb_z) % p:
+            return False
+    return True

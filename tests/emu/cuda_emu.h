@@ -99,6 +99,16 @@ static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return old;
 }
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
+    uint32_t expected = cmp;
+    __atomic_compare_exchange_n(p, &expected, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;
+}
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline uint32_t __brev(uint32_t x) {
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);

@@ -1,0 +1,9 @@
+"""Kernel-logic check of the whole device-resident prover on the CPU emulation: byte-identical
+to the oracle's golden proof at 2^5 (BLS12-381) - the GPU tests repeat this at 2^10..2^16."""
+import parity_cases as pc
+import prover_cases
+
+
+def test_prover_matches_golden_2p5(emu_lib):
+    with pc.env(APB_MSM_C=8, APB_NTT_MAX_LOG_TILE=4):
+        prover_cases.prove_case(emu_lib, prover_cases.golden_case(0, 5))

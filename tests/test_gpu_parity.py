@@ -58,3 +58,28 @@ def test_msm_windowed_geometry(gpu_lib):
     with pc.env(APB_MSM_STEP=64):
         pc.check_msm_tau(gpu_lib, 0, 3000)
         pc.check_msm_progression(gpu_lib, 0, 1 << 14)
+
+
+# ---- device-resident prover: byte-identical proofs ---------------------------------------------
+import prover_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("curve,degree", [(0, 5), (0, 8), (0, 10), (1, 6), (0, 12), (0, 14), (0, 16)])
+def test_prover_byte_identical_to_oracle(gpu_lib, curve, degree):
+    """BASELINE configs #1 (2^10) and #2 (2^16): the serialized Proof equals the oracle's golden vector"""
+    prover_cases.prove_case(gpu_lib, prover_cases.golden_case(curve, degree), repeat=2)
+
+
+def test_prover_without_discarded_commitments(gpu_lib):
+    """the 14 aw/saw commitments of prover.rs:579,606 are discarded by SonicKZG10::open: same bytes without them"""
+    prover_cases.prove_case(gpu_lib, prover_cases.golden_case(0, 10), faithful=False)
+
+
+def test_srs_from_tau_matches_oracle(gpu_lib):
+    from ark_plonk_b200 import encoding as enc, kzg
+    from oracle.curves import CURVES, powers_of_tau_g1
+    for curve in (0, 1):
+        ck = kzg.CommitterKey.from_tau(curve, 0xDEADBEEF12345, 300, lib=gpu_lib)
+        exp = enc.g1_affine_to_mont(curve, powers_of_tau_g1(CURVES[curve], 0xDEADBEEF12345, 300))
+        assert (ck.download(0, 300) == exp).all()
+        ck.close()
