@@ -54,6 +54,9 @@ class Lib:
         c.apb_msm_dev.argtypes = [vp, sz, vp, sz, ci, vp]
         c.apb_msm_batch_dev.argtypes = [vp, sz, vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), ci, vp]
         c.apb_g1_compress.argtypes = [ci, vp, vp]
+        c.apb_g1_add.argtypes = [ci, vp, vp, vp]
+        c.apb_msm_totals.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), ci]
+        c.apb_msm_totals.restype = None
         c.apb_domain_new.argtypes = [ci, C.c_uint32, C.POINTER(vp)]
         c.apb_domain_size.argtypes = [vp, C.POINTER(sz)]
         c.apb_domain_free.argtypes = [vp]
@@ -120,6 +123,18 @@ class Lib:
         v = C.c_double()
         self.check(self.c.apb_mul_bench(field, threads, blocks_per_sm, ilp, iters, C.byref(v)))
         return v.value
+
+    def msm_totals(self, reset: bool = False):
+        ms, pts = C.c_double(), C.c_ulonglong()
+        self.c.apb_msm_totals(C.byref(ms), C.byref(pts), 1 if reset else 0)
+        return ms.value, pts.value
+
+    def g1_add(self, curve: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        out = np.zeros(18, dtype=np.uint64)
+        self.check(self.c.apb_g1_add(curve, self._ptr(a), self._ptr(b), self._ptr(out)))
+        return out
 
     def imad_peak(self):
         w, n = C.c_double(), C.c_double()

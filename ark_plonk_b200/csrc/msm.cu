@@ -33,6 +33,8 @@ namespace apb {
 
 int g_num_sms = 1;
 int g_profile = 0;
+double g_acc_ms_total = 0.0;            // accumulated k_msm_accumulate time while profiling
+unsigned long long g_points_total = 0;  // scalars processed while profiling
 double g_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sort, accumulate, stitch, trees, copy+host epilogue
 
 static const int MAX_BATCH = 16;
@@ -715,6 +717,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
             g_phase_ms[i] = ms;
         }
+        g_acc_ms_total += g_phase_ms[1];
+        g_points_total += total;
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
 
@@ -832,6 +836,37 @@ extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, c
 }
 
 extern "C" void apb_set_profiling(int on) { g_profile = on; }
+extern "C" void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset) {
+    if (accumulate_ms) *accumulate_ms = g_acc_ms_total;
+    if (points) *points = g_points_total;
+    if (reset) { g_acc_ms_total = 0.0; g_points_total = 0; }
+}
+
+// host-side group addition of two normalised / Jacobian points (folding per-GPU partial sums)
+extern "C" int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_xyz[18], uint64_t out_xyz[18]) {
+    if (!a_xyz || !b_xyz || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_g1_add: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_g1_add: bad curve");
+    host::Group grp;
+    grp.f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fq381>() : host::Field::make<Fq377>();
+    const host::Field& f = grp.f;
+    auto load = [&](const uint64_t* j, host::Pt& p) {      // Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3)
+        memcpy(p.x, j, 48);
+        memcpy(p.y, j + 6, 48);
+        f.sqr(p.zz, j + 12);
+        f.mul(p.zzz, p.zz, j + 12);
+    };
+    host::Pt a, b, r;
+    load(a_xyz, a);
+    load(b_xyz, b);
+    grp.add(r, a, b);
+    uint64_t ax[6], ay[6];
+    memset(out_xyz, 0, 18 * 8);
+    if (!grp.to_affine(ax, ay, r)) return APB_OK;
+    memcpy(out_xyz, ax, 48);
+    memcpy(out_xyz + 6, ay, 48);
+    memcpy(out_xyz + 12, f.one, 48);
+    return APB_OK;
+}
 extern "C" void apb_msm_phase_ms(double out[4]) {
     for (int i = 0; i < 4; i++) out[i] = g_phase_ms[i];
 }

@@ -257,8 +257,21 @@ class Prover:
         return pow(root, 1 << (adicity - (size.bit_length() - 1)), p)
 
     # ---- prove -----------------------------------------------------------------------------
-    def prove(self, pk: ProverKey, wires_mont: np.ndarray, transcript_label: bytes = b"ark", faithful: bool = True,
-              trace: dict | None = None):
+    def upload_wires(self, pk: ProverKey, wires_mont) -> int:
+        """copies the (4, n, 4) witness columns into the key's arena (stays until the key is closed);
+        `wires_mont` may be a numpy array or an int host pointer (e.g. pinned memory)"""
+        off = pk.arena.alloc(4 * pk.n)
+        self._upload_wires(pk.arena, off, wires_mont, pk.n)
+        return off
+
+    def _upload_wires(self, arena, off, wires_mont, n):
+        if isinstance(wires_mont, int):
+            self.lib.check(self.lib.c.apb_dev_upload(arena.ptr(off), wires_mont, 4 * n * 32))
+        else:
+            arena.upload(off, np.ascontiguousarray(wires_mont).reshape(4 * n, 4))
+
+    def prove(self, pk: ProverKey, wires_mont, transcript_label: bytes = b"ark", faithful: bool = True,
+              trace: dict | None = None, wires_resident: int | None = None):
         """wires_mont: (4, n, 4) uint64 Montgomery wire values (w_l, w_r, w_o, w_4), padded to n.
         `faithful`: also issue the 14 commitments of prover.rs:579,606 whose results the reference
         discards (SonicKZG10::open ignores them) so that the MSM count matches the reference's 29."""
@@ -269,19 +282,23 @@ class Prover:
         mark = A.mark()
         T = trace if trace is not None else {}
         try:
-            return self._prove(pk, wires_mont, transcript_label, faithful, T, A, dom, dom4, n, N4, p, curve, lib)
+            return self._prove(pk, wires_mont, transcript_label, faithful, T, A, dom, dom4, n, N4, p, curve, lib,
+                               wires_resident)
         finally:
             lib.c.apb_dev_sync()
             A.release(mark)
 
-    def _prove(self, pk, wires_mont, label, faithful, T, A, dom, dom4, n, N4, p, curve, lib):
+    def _prove(self, pk, wires_mont, label, faithful, T, A, dom, dom4, n, N4, p, curve, lib, wires_resident=None):
         tr = Transcript(lib, curve, label)
         tr.append_bytes(b"pi", (0).to_bytes(8, "little"))
         omega = self._root_of_unity(n)
 
         # -- round 1: wire polynomials (prover.rs:188-220)
-        w_ev = A.alloc(4 * n)
-        A.upload(w_ev, np.ascontiguousarray(wires_mont).reshape(4 * n, 4))
+        if wires_resident is not None:
+            w_ev = wires_resident
+        else:
+            w_ev = A.alloc(4 * n)
+            self._upload_wires(A, w_ev, wires_mont, n)
         w_poly = A.alloc(4 * n)
         self._ntt(dom, NTT_IFFT, A, w_ev, n, w_poly, batch=4)
         wp = [w_poly + c * n for c in range(4)]
@@ -303,15 +320,15 @@ class Prover:
                                            A.ptr(wv[3]), A.ptr(t_comp), zeta_m.ctypes.data, A.ptr(f_comp), n))
         f_poly = A.alloc(n)
         self._ntt(dom, NTT_IFFT, A, f_comp, n, f_poly)
-        f_comm = self._commit(A, [f_poly], [n])[0]
-        tr.append_bytes(b"f", f_comm[1])
+        # combine_split needs no further challenge, so f, h1, h2 are committed in one batched pass
+        # (the reference issues three PC::commit calls, prover.rs:290,313,316); transcript order kept
         h_ev = A.alloc(2 * n)
         lib.check(lib.c.apb_plonk_combine_split(curve, A.ptr(t_comp), A.ptr(f_comp), n, A.ptr(h_ev), A.ptr(h_ev + n)))
         h_poly = A.alloc(2 * n)
         self._ntt(dom, NTT_IFFT, A, h_ev, n, h_poly, batch=2)
         h1_poly, h2_poly = h_poly, h_poly + n
-        h1_comm = self._commit(A, [h1_poly], [n])[0]
-        h2_comm = self._commit(A, [h2_poly], [n])[0]
+        f_comm, h1_comm, h2_comm = self._commit(A, [f_poly, h1_poly, h2_poly], [n] * 3)
+        tr.append_bytes(b"f", f_comm[1])
         tr.append_bytes(b"h1", h1_comm[1])
         tr.append_bytes(b"h2", h2_comm[1])
 
@@ -333,14 +350,13 @@ class Prover:
         lib.check(lib.c.apb_plonk_perm_z(dom._h, wires_p, sig_p, beta_m.ctypes.data, gamma_m.ctypes.data, A.ptr(z_ev)))
         z_poly = A.alloc(n)
         self._ntt(dom, NTT_IFFT, A, z_ev, n, z_poly)
-        z_comm = self._commit(A, [z_poly], [n])[0]
-        tr.append_bytes(b"z", z_comm[1])
         z2_ev = A.alloc(n)
         lib.check(lib.c.apb_plonk_lookup_z2(dom._h, A.ptr(f_comp), A.ptr(t_comp), A.ptr(h_ev), A.ptr(h_ev + n),
                                             delta_m.ctypes.data, eps_m.ctypes.data, A.ptr(z2_ev)))
         z2_poly = A.alloc(n)
         self._ntt(dom, NTT_IFFT, A, z2_ev, n, z2_poly)
-        z2_comm = self._commit(A, [z2_poly], [n])[0]
+        z_comm, z2_comm = self._commit(A, [z_poly, z2_poly], [n] * 2)       # prover.rs:362,388 in one pass
+        tr.append_bytes(b"z", z_comm[1])                                    # z2 is not absorbed (prover.rs:387-389)
 
         # -- round 4: quotient (prover.rs:398-475, quotient_poly.rs:34-178)
         alpha = tr.challenge(b"alpha"); tr.append_fr(b"alpha", alpha)
@@ -420,21 +436,23 @@ class Prover:
         # -- openings (prover.rs:563-618; sonic_pc::open: p = sum challenge^i p_i, witness = p / (X - z))
         aw_challenge = tr.challenge(b"aggregate_witness")
         aw_polys = [lin_poly, P["left_sigma"], P["right_sigma"], P["out_sigma"], f_poly, h2_poly, table_poly] + wp
-        if faithful:
-            self._commit(A, aw_polys[:7], [n] * 7)
         comb = A.alloc(n)
         wit = A.alloc(n)
         self._lincomb(A, aw_polys, [n] * len(aw_polys), [pow(aw_challenge, i, p) for i in range(len(aw_polys))], comb, n)
         zc_m, zw_m = _mont(curve, zc), _mont(curve, zw)
         lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb), n, zc_m.ctypes.data, A.ptr(wit)))
-        aw_open = self._commit(A, [wit], [n - 1])[0]
+        if faithful:       # PC::commit(aw_polys) (prover.rs:579, results unused by open) + the opening MSM, one pass
+            aw_open = self._commit(A, aw_polys[:7] + [wit], [n] * 7 + [n - 1])[7]
+        else:
+            aw_open = self._commit(A, [wit], [n - 1])[0]
         saw_challenge = tr.challenge(b"aggregate_witness")
         saw_polys = [z_poly, wp[0], wp[1], wp[3], h1_poly, z2_poly, table_poly]
-        if faithful:
-            self._commit(A, saw_polys, [n] * 7)
         self._lincomb(A, saw_polys, [n] * 7, [pow(saw_challenge, i, p) for i in range(7)], comb, n)
         lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb), n, zw_m.ctypes.data, A.ptr(wit)))
-        saw_open = self._commit(A, [wit], [n - 1])[0]
+        if faithful:
+            saw_open = self._commit(A, saw_polys + [wit], [n] * 7 + [n - 1])[7]
+        else:
+            saw_open = self._commit(A, [wit], [n - 1])[0]
 
         if T is not None and T.get("want"):
             T.update(zeta=zeta, beta=beta, gamma=gamma, delta=delta, epsilon=epsilon, alpha=alpha, lookup_sep=lookup_sep,

@@ -93,6 +93,10 @@ int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t
                       const size_t* base_offsets, const size_t* lens, int scalars_are_montgomery,
                       uint64_t* out_xyz);
 
+/* out = a + b for two points in the (X, Y, Z) form apb_msm returns; folds per-GPU partial sums of a
+ * point-split MSM (host side, a handful of field operations) */
+int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_xyz[18], uint64_t out_xyz[18]);
+
 /* ark-serialize compressed G1Affine (48 bytes; flags in the top bits of the last byte):
  * what `Commitment` contributes to the transcript (plonk-core/src/transcript.rs:27-33). */
 int apb_g1_compress(int curve, const uint64_t xyz[18], uint8_t out[48]);
@@ -178,6 +182,8 @@ int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t i
  * (recorded only after apb_set_profiling(1)) */
 void apb_set_profiling(int on);
 void apb_msm_phase_ms(double out[4]);
+/* totals since the last reset while profiling: k_msm_accumulate milliseconds and scalars processed */
+void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset);
 /* milliseconds of device time of the last blocking apb_msm / apb_ntt call (CUDA events) */
 double apb_last_device_ms(void);
 
