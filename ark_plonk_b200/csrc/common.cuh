@@ -65,10 +65,12 @@ APB_D void store_fp(void* base, size_t idx, const Fp<P>& a) {
 struct Curve381 {
     typedef Fr381 FR;
     typedef Fq381 FQ;
+    typedef Fq381_28 FQ28;
 };
 struct Curve377 {
     typedef Fr377 FR;
     typedef Fq377 FQ;
+    typedef Fq377_28 FQ28;
 };
 
 }  // namespace apb

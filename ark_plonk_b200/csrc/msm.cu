@@ -27,7 +27,9 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fp28.cuh"
 #include "host_ec.hpp"
+#include "scan_u32.cuh"
 
 namespace apb {
 
@@ -256,6 +258,102 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* en
     }
 }
 
+// Same walk with the accumulator in reduced radix (fp28.cuh): the resident table holds x*2^392
+// mod p, the mixed addition runs on carry-free IMAD.WIDE columns, and a flushed bucket is mapped
+// back to the library-wide 2^384 Montgomery form.
+template <class P28>
+__device__ __noinline__ void flush28(const XYZZ28<P28>& acc, void* dst, uint64_t idx) {
+    typedef typename P28::Base FQ;
+    XYZZ<FQ> o;
+    if (acc.inf) {
+        o = XYZZ<FQ>::identity();
+    } else {
+        o.x = acc.x.to_mont384();
+        o.y = acc.y.to_mont384();
+        o.zz = acc.zz.to_mont384();
+        o.zzz = acc.zzz.to_mont384();
+    }
+    store_xyzz<FQ>(dst, idx, o);
+}
+
+template <class P28, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate28(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
+                                                                const void* bases, uint32_t E, void* bucket_sums, void* partials,
+                                                                int32_t* part_bucket) {
+    typedef typename P28::Base FQ;
+    typedef Fp<FQ> W;             // packed 12-word records as loaded
+    typedef Fp28<P28> F;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t M = offsets[nbuckets];
+    part_bucket[2 * t] = -1;
+    part_bucket[2 * t + 1] = -1;
+    uint64_t pos = t * E;
+    if (pos >= M) return;
+    const uint64_t end = pos + E < M ? pos + E : M;
+    uint32_t lo = 0, hi = nbuckets;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    while (offsets[b + 1] <= pos) b++;
+    uint32_t e_cur = entries[pos];
+    W px, py;
+    load_affine<FQ>(bases, e_cur & 0x7fffffffu, px, py);
+    uint64_t bstart = offsets[b], bend = offsets[b + 1], run_start = pos;
+    XYZZ28<P28> acc;
+    acc.set_identity();
+    while (pos < end) {
+        uint32_t e_nxt = 0;
+        W nx, ny;
+        const bool more = pos + 1 < end;
+        if (more) {
+            e_nxt = entries[pos + 1];
+            load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
+        }
+        if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
+            F ax = F::from_words(px.v), ay = F::from_words(py.v);
+            if (e_cur >> 31) ay = ay.neg_canonical();
+            acc.add_affine(ax, ay);
+        }
+        pos++;
+        if (pos == bend || pos == end) {                     // run finished: flush
+            const bool head = run_start == bstart, tail = pos == bend;
+            if (head && tail) {
+                flush28<P28>(acc, bucket_sums, b);
+            } else if (head) {
+                flush28<P28>(acc, partials, 2 * t + 1);
+                part_bucket[2 * t + 1] = (int32_t)b;
+            } else {
+                flush28<P28>(acc, partials, 2 * t);
+                part_bucket[2 * t] = (int32_t)b;
+            }
+            if (pos < end) {
+                b++;
+                while (offsets[b + 1] <= pos) b++;
+                bstart = offsets[b];
+                bend = offsets[b + 1];
+                run_start = pos;
+                acc.set_identity();
+            }
+        }
+        __syncwarp();
+        if (more) { e_cur = e_nxt; px = nx; py = ny; }
+    }
+}
+
+// in place: table entries x*2^384 -> x*2^392 (mod p)
+template <class P28>
+__global__ void k_table_to392(void* bases, uint64_t count) {
+    typedef typename P28::Base FQ;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fp<FQ> c;
+#pragma unroll
+    for (int k = 0; k < 12; k++) c.v[k] = P28::to392(k);
+    store_fp<FQ>(bases, i, load_fp<FQ>(bases, i) * c);
+}
+
 // stitch buckets that straddle chunk borders: the chunk holding the head piece sums the rest
 template <class FQ>
 __global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uint32_t E, uint64_t nthreads, void* bucket_sums,
@@ -414,10 +512,13 @@ struct apb_ck_s {
     int curve;
     size_t n;
     uint32_t F, step;
-    void* bases;                   // F * n affine points
+    void* bases;                   // F * n affine points (x*2^392 domain when radix == 28)
+    void* bases_orig;              // the n points as uploaded (download / diagnostics)
+    int radix;                     // 28: reduced-radix accumulate (default); 32: carry-chain accumulate
     // workspace (grown on demand)
     void* d_scalars; size_t scalars_cap;
     uint32_t *counts, *offsets, *cursors; size_t buckets_cap;
+    uint32_t* scan_tmp; size_t scan_tmp_cap;
     uint32_t* entries; size_t entries_cap;
     void* bucket_sums; size_t sums_cap;
     void* partials; int32_t* part_bucket; size_t partial_cap;
@@ -468,6 +569,15 @@ static int ck_precompute(apb_ck_s* ck) {
     unsigned blocks = (unsigned)((ck->n + 127) / 128);
     if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
     else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
+    ck->radix = 28;
+    if (const char* e = getenv("APB_MSM_RADIX")) ck->radix = atoi(e) == 32 ? 32 : 28;
+    if (ck->radix == 28) {
+        APB_CUDA_TRY(cudaMalloc(&ck->bases_orig, ck->n * 96));
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases_orig, ck->bases, ck->n * 96, cudaMemcpyDeviceToDevice, g_stream));
+        const uint64_t count = (uint64_t)ck->n * ck->F * 2;
+        if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_table_to392<Fq381_28>, (unsigned)((count + 127) / 128), 128, 0, ck->bases, count);
+        else APB_KLAUNCH(k_table_to392<Fq377_28>, (unsigned)((count + 127) / 128), 128, 0, ck->bases, count);
+    }
     APB_CHECK_LAUNCH();
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
@@ -515,7 +625,8 @@ extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const ui
 extern "C" int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t* out_xy) {
     if (!ck || ck->magic != CK_MAGIC || !out_xy) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_download: bad handle");
     if (first + count > ck->n) return set_err(APB_ERR_INVALID_ARG, "apb_ck_download: range exceeds key size");
-    APB_CUDA_TRY(cudaMemcpyAsync(out_xy, (const char*)ck->bases + first * 96, count * 96, cudaMemcpyDeviceToHost, g_stream));
+    const char* src = (const char*)(ck->bases_orig ? ck->bases_orig : ck->bases);
+    APB_CUDA_TRY(cudaMemcpyAsync(out_xy, src + first * 96, count * 96, cudaMemcpyDeviceToHost, g_stream));
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
 }
@@ -544,7 +655,8 @@ extern "C" int apb_ck_size(apb_ck_t ck, size_t* n) {
 extern "C" void apb_ck_free(apb_ck_t ck) {
     if (!ck || ck->magic != CK_MAGIC) return;
     // offsets / cursors / stage_b are interior pointers of counts / stage_a
-    cudaFree(ck->bases); cudaFree(ck->d_scalars); cudaFree(ck->counts);
+    cudaFree(ck->bases); cudaFree(ck->bases_orig); cudaFree(ck->d_scalars); cudaFree(ck->counts);
+    cudaFree(ck->scan_tmp);
     cudaFree(ck->entries); cudaFree(ck->bucket_sums); cudaFree(ck->partials);
     cudaFree(ck->part_bucket); cudaFree(ck->stage_a); cudaFree(ck->jobs);
     if (ck->h_out) cudaFreeHost(ck->h_out);
@@ -621,7 +733,9 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if (const char* e = getenv("APB_MSM_ACC_VARIANT")) acc_variant = atoi(e) ? 1 : 0;
 #ifndef APB_EMU
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        if (ck->radix == 28) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate28<typename CV::FQ28, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 3>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
 #endif
     }
@@ -635,6 +749,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
 
     int rc;
     if ((rc = grow(&ck->counts, &ck->buckets_cap, (size_t)(nbuckets + 1) * 4 * 3)) != APB_OK) return rc;
+    if ((rc = grow(&ck->scan_tmp, &ck->scan_tmp_cap, ((size_t)nbuckets / 1024 + 8) * 4)) != APB_OK) return rc;
     ck->offsets = ck->counts + (nbuckets + 1);
     ck->cursors = ck->offsets + (nbuckets + 1);
     if ((rc = grow(&ck->entries, &ck->entries_cap, (size_t)Mmax * 4)) != APB_OK) return rc;
@@ -688,13 +803,21 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     auto k_hist = k_msm_digits<FR, 0>;
     auto k_scatter = k_msm_digits<FR, 1>;
     APB_KLAUNCH(k_hist, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
-    APB_KLAUNCH(k_scan_exclusive, 1, SCAN_THREADS, 0, (const uint32_t*)ck->counts, ck->offsets, nbuckets);
+    {   // offsets = exclusive scan of counts; offsets[nbuckets] = number of sorted entries
+        int rc2 = u32_scan(ck->counts, ck->offsets, nbuckets, ck->scan_tmp, ck->offsets + nbuckets);
+        if (rc2 != APB_OK) return rc2;
+    }
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
     if (g_profile) cudaEventRecord(ev[1], g_stream);
     // 4. accumulate  5. stitch
+    typedef typename CV::FQ28 FQ28;
+    auto k_acc28 = k_msm_accumulate28<FQ28, 2>;
     auto k_acc2 = k_msm_accumulate<FQ, 2>;
     auto k_acc3 = k_msm_accumulate<FQ, 3>;
-    if (acc_variant == 0)
+    if (ck->radix == 28)
+        APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    else if (acc_variant == 0)
         APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                     (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     else

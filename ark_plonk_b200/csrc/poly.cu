@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "host_ec.hpp"
+#include "scan_u32.cuh"
 
 namespace apb {
 
@@ -307,36 +308,6 @@ __global__ void k_cs_fill(const void* tv, const uint32_t* offsets, uint64_t n, v
     o[2 * p] = t[2 * lo];
     o[2 * p + 1] = t[2 * lo + 1];
 }
-// multi-block exclusive scan of u32 (block = 1024 elements), three small kernels
-__global__ void __launch_bounds__(256) k_u32_scan_block(const uint32_t* in, uint32_t* out, uint32_t* block_tot, uint64_t n) {
-    __shared__ uint32_t sm[256];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t base = ((uint64_t)blockIdx.x * 256 + tid) * 4;
-    uint32_t e[4], run = 0;
-    for (int j = 0; j < 4; j++) { e[j] = base + j < n ? in[base + j] : 0; run += e[j]; }
-    sm[tid] = run;
-    __syncthreads();
-    for (uint32_t off = 1; off < 256; off <<= 1) {
-        uint32_t v = tid >= off ? sm[tid - off] : 0;
-        __syncthreads();
-        sm[tid] += v;
-        __syncthreads();
-    }
-    uint32_t acc = tid ? sm[tid - 1] : 0;
-    for (int j = 0; j < 4; j++) { if (base + j < n) out[base + j] = acc; acc += e[j]; }
-    if (tid == 255) block_tot[blockIdx.x] = sm[255];
-}
-__global__ void k_u32_scan_totals(uint32_t* block_tot, uint32_t nb, uint32_t* total) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t acc = 0;
-    for (uint32_t i = 0; i < nb; i++) { uint32_t e = block_tot[i]; block_tot[i] = acc; acc += e; }
-    *total = acc;
-}
-__global__ void k_u32_scan_apply(uint32_t* out, const uint32_t* block_tot, uint64_t n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] += block_tot[i >> 10];
-}
-
 // ---- quotient -------------------------------------------------------------------------------
 struct QuotientArgs {
     const void *wl, *wr, *wo, *w4, *z, *z2, *f, *table, *h1, *h2, *pi;
@@ -626,15 +597,6 @@ extern "C" int apb_plonk_lookup_f(int curve, const void* q_lookup, const void* w
     APB_REQUIRE_INIT();
     DISPATCH_FR(curve, APB_KLAUNCH(k_lookup_f<Fr381>, nblk(n, 128), 128, 0, q_lookup, wl, wr, wo, w4, t_comp, mk4(zeta), d_out, (uint64_t)n),
                 APB_KLAUNCH(k_lookup_f<Fr377>, nblk(n, 128), 128, 0, q_lookup, wl, wr, wo, w4, t_comp, mk4(zeta), d_out, (uint64_t)n));
-    APB_CHECK_LAUNCH();
-    return APB_OK;
-}
-
-static int u32_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* block_tot, uint32_t* total) {
-    const unsigned nb = (unsigned)((n + 1023) / 1024);
-    APB_KLAUNCH(k_u32_scan_block, nb, 256, 0, in, out, block_tot, (uint64_t)n);
-    APB_KLAUNCH(k_u32_scan_totals, 1, 32, 0, block_tot, nb, total);
-    APB_KLAUNCH(k_u32_scan_apply, nblk(n, 256), 256, 0, out, (const uint32_t*)block_tot, (uint64_t)n);
     APB_CHECK_LAUNCH();
     return APB_OK;
 }

@@ -154,6 +154,28 @@ def check_msm_progression(lib, curve, n, seed=5, k=1):
         ck.close()
 
 
+def check_msm_duplicates(lib, curve, seed=9):
+    """equal points meeting in one bucket (doubling branch of the mixed addition) and P + (-P) (identity)"""
+    cv = CURVES[curve]
+    r = cv.fr.p
+    rnd = random.Random(seed)
+    base = [cv.mul(cv.G, rnd.randrange(1, r)) for _ in range(3)]
+    pts = [base[0], base[0], base[1], base[1], base[2], base[0], None, base[1]]
+    cases = [
+        [5, 5, 7, r - 7, 1, 5, 9, 0],                 # 3 x the same point into one bucket; P + (-P)
+        [12345] * 8,
+        [r - 1, 1, r - 2, 2, 0, r - 1, 3, 4],
+        [1 << 16, 1 << 16, (1 << 32) + 1, (1 << 32) + 1, 0, 1 << 16, 1, 1 << 32],
+    ]
+    ck = kzg.CommitterKey(curve, enc.g1_affine_to_mont(curve, pts), lib=lib)
+    try:
+        for s in cases:
+            out = kzg.multi_scalar_mul(ck, enc.ints_to_limbs(s, 4))
+            assert enc.g1_from_xyz(curve, out) == cv.msm_naive(pts, s), s
+    finally:
+        ck.close()
+
+
 def edge_scalars(curve, n):
     r = FR[curve].p
     base = [0, 1, 2, r - 1, r - 2, (r - 1) // 2, (r + 1) // 2, 5, 0, 0, 0, 7, 1 << 200, (1 << 250) + 5, 12345,
