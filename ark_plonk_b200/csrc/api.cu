@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "fp28.cuh"
 
 namespace apb {
 
@@ -99,6 +100,27 @@ __global__ void k_mul_bench(void* out, uint32_t iters) {
     if (s.v[0] == 0x12345 && s.v[1] == 77) store_fp<P>(out, 0, s);
 }
 
+// same for the reduced-radix product (fp28.cuh)
+template <class P28, int ILP>
+__global__ void k_mul_bench28(void* out, uint32_t iters) {
+    Fp28<P28> x[ILP], y = Fp28<P28>::one();
+    y.l[1] += 12345;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        x[k] = Fp28<P28>::one();
+        x[k].l[0] += threadIdx.x + k;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = x[k] * y;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+        for (int i = 0; i < 14; i++) s ^= x[k].l[i];
+    if (s == 0x12345) ((uint32_t*)out)[0] = s;
+}
+
 }  // namespace apb
 
 using namespace apb;
@@ -132,9 +154,35 @@ static int run_mul_bench(int threads, int blocks_per_sm, int ilp, uint32_t iters
     return APB_OK;
 }
 
+static int run_mul_bench28(int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
+    void* d_out = nullptr;
+    APB_CUDA_TRY(cudaMalloc(&d_out, 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    unsigned blocks = (unsigned)(g_num_sms * blocks_per_sm);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, g_stream);
+        auto k1 = k_mul_bench28<Fq381_28, 1>;
+        auto k2 = k_mul_bench28<Fq381_28, 2>;
+        if (ilp == 1) APB_KLAUNCH(k1, blocks, threads, 0, d_out, iters);
+        else APB_KLAUNCH(k2, blocks, threads, 0, d_out, iters);
+        cudaEventRecord(e1, g_stream);
+        APB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *muls_per_s = (double)blocks * threads * iters * (ilp == 1 ? 1 : 2) / (best * 1e-3);
+    return APB_OK;
+}
+
 extern "C" int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
     APB_REQUIRE_INIT();
     if (!muls_per_s) return set_err(APB_ERR_INVALID_ARG, "apb_mul_bench: null out");
+    if (field == 4) return run_mul_bench28(threads, blocks_per_sm, ilp, iters, muls_per_s);
     switch (field) {
         case 0: return run_mul_bench<Fr381>(threads, blocks_per_sm, ilp, iters, muls_per_s);
         case 1: return run_mul_bench<Fq381>(threads, blocks_per_sm, ilp, iters, muls_per_s);

@@ -569,8 +569,12 @@ static int ck_precompute(apb_ck_s* ck) {
     unsigned blocks = (unsigned)((ck->n + 127) / 128);
     if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
     else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
-    ck->radix = 28;
-    if (const char* e = getenv("APB_MSM_RADIX")) ck->radix = atoi(e) == 32 ? 32 : 28;
+    // 32: carry-chained 32-bit limbs (default, 30.9 G Fq-mul/s measured); 28: reduced-radix experiment
+    // (carry-free IMAD.WIDE columns) - measured SLOWER on sm_100a (20.6 G mul/s: the plain IMAD.WIDE
+    // with distinct register operands and the extra ALU work do not dual-issue as hoped), kept
+    // selectable for the record: profiles/r01_mul_bench_radix28.json
+    ck->radix = 32;
+    if (const char* e = getenv("APB_MSM_RADIX")) ck->radix = atoi(e) == 28 ? 28 : 32;
     if (ck->radix == 28) {
         APB_CUDA_TRY(cudaMalloc(&ck->bases_orig, ck->n * 96));
         APB_CUDA_TRY(cudaMemcpyAsync(ck->bases_orig, ck->bases, ck->n * 96, cudaMemcpyDeviceToDevice, g_stream));

@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""BASELINE configs #4 / #5: standalone G1 MSM sweep (2^16..2^26, both curves) and Fr NTT sweep
+(2^16..2^28) on one B200.  Bases = [tau^i]G generated on the device.  Results are checked:
+MSM against [sum s_i tau^i]G (one host scalar multiplication), NTT by round trip on a slice."""
+import json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from ark_plonk_b200 import encoding as enc, kzg, synth
+from ark_plonk_b200._lib import get_lib
+from ark_plonk_b200.domain import Radix2EvaluationDomain
+lib = get_lib(); lib.init(0)
+wide, _ = lib.imad_peak()
+out = {"imad_wide_per_s": wide, "msm": [], "ntt": []}
+stream = torch.cuda.ExternalStream(lib.c.apb_stream())
+max_msm = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+max_ntt = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+lib.set_profiling(True)
+for curve in (0, 1):
+    for log_n in ([16, 18, 20, 22, 24, 26] if curve == 0 else [18, 22]):
+        if log_n > max_msm: continue
+        n = 1 << log_n
+        tau = 0xABCDEF0123456789ABCDEF + curve
+        t0 = time.time(); ck = kzg.CommitterKey.from_tau(curve, tau, n); t_setup = time.time() - t0
+        S = synth.seeded_scalars(curve, n, seed=b"sweep%d" % log_n)
+        dS = torch.from_numpy(S.view(np.int64)).cuda()
+        o = np.zeros(18, dtype=np.uint64)
+        ts, ph = [], []
+        for i in range(5):
+            lib.check(lib.c.apb_msm_dev(ck._h, 0, dS.data_ptr(), n, 0, o.ctypes.data))
+            if i >= 2: ts.append(lib.last_device_ms()); ph.append(lib.msm_phase_ms())
+        ms = float(np.median(ts))
+        ok = None
+        if log_n <= 20:       # closed form check (python big ints: keep it cheap)
+            r = enc.FR_MODULUS[curve]
+            e, tp = 0, 1
+            for s in synth.limbs_to_int_list(S):
+                e = (e + s * tp) % r; tp = tp * tau % r
+            ok = enc.g1_from_xyz(curve, o) == synth.scalar_mul(curve, synth.G1_GENERATOR[curve], e)
+        rec = dict(curve=curve, log_n=log_n, ms=ms, mpts=n / ms / 1e3, accumulate_ms=float(np.median([p["accumulate"] for p in ph])),
+                   sort_ms=float(np.median([p["sort"] for p in ph])), reduce_ms=float(np.median([p["reduce"] for p in ph])),
+                   imad_frac=n * 48000 / (ms * 1e-3) / wide, setup_s=t_setup, verified=ok)
+        print(rec, flush=True); out["msm"].append(rec)
+        ck.close(); del dS
+for curve in (0, 1):
+    for log_n in ([16, 18, 20, 22, 24, 26, 28] if curve == 0 else [20, 24]):
+        if log_n > max_ntt: continue
+        n = 1 << log_n
+        d = Radix2EvaluationDomain(curve, n)
+        x = torch.randint(0, 2**60, (n, 4), dtype=torch.int64, device="cuda")
+        y = torch.empty_like(x)
+        rec = dict(curve=curve, log_n=log_n)
+        for kind, name in ((0, "fft"), (2, "coset_fft")):
+            for _ in range(2): d.ntt_dev(kind, x.data_ptr(), n, y.data_ptr(), sync=True)
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(); d.ntt_dev(kind, x.data_ptr(), n, y.data_ptr()); e1.record()
+                e1.synchronize(); ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            rec[name + "_ms"] = ms; rec[name + "_gbs"] = 2 * n * 32 / (ms * 1e-3) / 1e9
+            rec[name + "_imad_frac"] = (n / 2 * log_n + n) * 136 / (ms * 1e-3) / wide
+        # round trip on the device: coset_ifft(coset_fft(x)) == x
+        d.ntt_dev(2, x.data_ptr(), n, y.data_ptr(), sync=True); d.ntt_dev(3, y.data_ptr(), n, y.data_ptr(), sync=True)
+        rec["roundtrip_ok"] = bool(torch.equal(x[: 1 << 16], y[: 1 << 16]) and torch.equal(x[-(1 << 16):], y[-(1 << 16):]))
+        print(rec, flush=True); out["ntt"].append(rec)
+        d.close(); del x, y
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "big_sweep.json"), "w"), indent=1)

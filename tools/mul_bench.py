@@ -8,9 +8,9 @@ from ark_plonk_b200._lib import get_lib
 lib = get_lib(); lib.init(0)
 wide, n32 = lib.imad_peak()
 res = {"imad_wide_per_s": wide, "rows": []}
-for field, name, imads in ((1, "Fq381", 300), (0, "Fr381", 136)):
+for field, name, imads in ((4, "Fq381_28", 300), (1, "Fq381", 300)):
     for threads, bps in ((128, 1), (128, 2), (128, 3), (128, 4), (128, 8), (256, 8)):
-        for ilp in (1, 2, 4):
+        for ilp in (1, 2):
             m = lib.mul_bench(field, threads, bps, ilp, 1500)
             row = dict(field=name, threads_per_sm=threads * bps, ilp=ilp, muls_per_s=m, imad_frac=m * imads / wide)
             res["rows"].append(row)
