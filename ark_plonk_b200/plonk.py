@@ -134,6 +134,7 @@ class Prover:
         self.p = enc.FR_MODULUS[curve]
         self.msm_calls = 0
         self.ntt_calls = 0
+        self.phase_log = None          # set to a list to record (k, per-phase ms) of every commit call
 
     # ---- thin wrappers -----------------------------------------------------------------------
     def _ntt(self, dom, kind, arena, src, in_len, dst, batch=1, in_stride=None, out_stride=None):
@@ -153,6 +154,8 @@ class Prover:
         ln = (C.c_size_t * k)(*lens)
         out = np.zeros((k, 18), dtype=np.uint64)
         self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, k, arena.base, so, bo, ln, 1, out.ctypes.data))
+        if self.phase_log is not None:
+            self.phase_log.append((k, self.lib.last_device_ms(), self.lib.msm_phase_ms()))
         return [(out[i], self.lib.g1_compress(self.curve, out[i])) for i in range(k)]
 
     def _lincomb(self, arena, offs, lens, scalars, dst, out_len):

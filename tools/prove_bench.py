@@ -25,6 +25,14 @@ for degree in [int(a) for a in sys.argv[1:]] or [16, 18]:
             blob = pr.prove(pk, wires, b"ark", faithful=faithful)
             ts.append((time.perf_counter() - t0) * 1e3)
         times.append(ts)
+    lib.set_profiling(True)
+    pr.phase_log = []
+    t0 = time.perf_counter(); pr.prove(pk, wires, b"ark", faithful=True); t_prof = (time.perf_counter() - t0) * 1e3
+    for k, ms, ph in pr.phase_log:
+        print("   commit k=%d total %.3f ms  %s" % (k, ms, {a: round(b, 3) for a, b in ph.items()}), flush=True)
+    print("   sum of commit calls %.2f ms of %.2f ms" % (sum(m for _, m, _ in pr.phase_log), t_prof), flush=True)
+    pr.phase_log = None
+    lib.set_profiling(False)
     rec = dict(degree=degree, n=circ.n, rows=circ.rows, build_s=t_build, srs_s=t_srs, preprocess_s=t_pre,
                prove_ms_faithful=float(np.median(times[0][2:])), prove_ms_no_dead_commits=float(np.median(times[1][2:])),
                all=times, sha=hashlib.sha256(blob).hexdigest())
