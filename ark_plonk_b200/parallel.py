@@ -58,3 +58,90 @@ def sharded_msm(ck: ShardedCommitterKey, scalars: np.ndarray, montgomery: bool =
     for r in range(1, ck.world):
         acc = ck.lib.g1_add(ck.curve, acc, parts[r])
     return acc
+
+
+class DistributedCommitter:
+    """Per-polynomial task split of `PC::commit` over the ranks of a process group (SURVEY.md 8e,
+    "batched prove").  Every rank holds the full commitment key resident; rank 0 runs the prover and,
+    for each batch of k polynomials, broadcasts the coefficient vectors (k x n x 32 B over
+    NVLink), every rank multiplies the polynomials j with j % world == rank, and the normalised
+    results (144 B each) are combined with one all-reduce.  Workers sit in `serve()`.
+    The transcript, NTTs and pointwise kernels stay on rank 0 (they depend on each commitment).
+    """
+    OP_STOP, OP_COMMIT = 0, 1
+
+    def __init__(self, curve: int, ck: "kzg.CommitterKey", n_max: int, k_max: int = 8, group=None, device: str = "cuda",
+                 lib: Lib | None = None):
+        self.curve, self.ck, self.n, self.k_max, self.group, self.device = curve, ck, n_max, k_max, group, device
+        self.lib = lib or get_lib()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.header = torch.zeros(2 + k_max, dtype=torch.int64, device=device)
+        self.stage = torch.zeros(k_max * n_max * 4, dtype=torch.int64, device=device)
+        self.results = torch.zeros(k_max * 18, dtype=torch.int64, device=device)
+        self._stream = None
+        if device == "cuda":
+            self._stream = torch.cuda.ExternalStream(self.lib.c.apb_stream())
+
+    def _ctx(self):
+        import contextlib
+        return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
+
+    def _local_msms(self, k: int, lens) -> None:
+        """MSMs of the staged polynomials owned by this rank -> self.results rows (others zero)"""
+        import ctypes as C
+        mine = [j for j in range(k) if j % self.world == self.rank]
+        self.results.zero_()
+        if mine:
+            m = len(mine)
+            so = (C.c_size_t * m)(*[j * self.n for j in mine])
+            bo = (C.c_size_t * m)(*([0] * m))
+            ln = (C.c_size_t * m)(*[int(lens[j]) for j in mine])
+            out = np.zeros((m, 18), dtype=np.uint64)
+            self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, m, self.stage.data_ptr(), so, bo, ln, 1, out.ctypes.data))
+            host = torch.from_numpy(out.view(np.int64))
+            for i, j in enumerate(mine):
+                self.results[j * 18:(j + 1) * 18].copy_(host[i])
+
+    def commit(self, arena, offs, lens) -> np.ndarray:
+        """rank 0: commitments of the k polynomials at arena offsets `offs` -> (k, 18) uint64"""
+        k = len(offs)
+        out = np.zeros((k, 18), dtype=np.uint64)
+        for base in range(0, k, self.k_max):
+            kk = min(self.k_max, k - base)
+            with self._ctx():
+                hdr = [self.OP_COMMIT, kk] + [int(x) for x in lens[base:base + kk]] + [0] * (self.k_max - kk)
+                self.header.copy_(torch.tensor(hdr, dtype=torch.int64))
+                for j in range(kk):
+                    self.stage[j * self.n * 4:(j * self.n + int(lens[base + j])) * 4].copy_(arena.view(offs[base + j], int(lens[base + j])))
+                dist.broadcast(self.header, src=0, group=self.group)
+                dist.broadcast(self.stage[: kk * self.n * 4], src=0, group=self.group)
+                if self._stream is not None:
+                    self._stream.synchronize()
+                self._local_msms(kk, lens[base:base + kk])
+                dist.all_reduce(self.results, group=self.group)
+                out[base:base + kk] = self.results[: kk * 18].cpu().numpy().view(np.uint64).reshape(kk, 18)
+        return out
+
+    def serve(self) -> int:
+        """worker ranks: answer commit requests until rank 0 calls `shutdown`; returns #batches served"""
+        served = 0
+        while True:
+            with self._ctx():
+                dist.broadcast(self.header, src=0, group=self.group)
+                hdr = self.header.cpu().tolist()
+                if hdr[0] == self.OP_STOP:
+                    return served
+                kk = hdr[1]
+                dist.broadcast(self.stage[: kk * self.n * 4], src=0, group=self.group)
+                if self._stream is not None:
+                    self._stream.synchronize()
+                self._local_msms(kk, hdr[2:2 + kk])
+                dist.all_reduce(self.results, group=self.group)
+            served += 1
+
+    def shutdown(self):
+        if self.world > 1 and self.rank == 0:
+            with self._ctx():
+                self.header.zero_()
+                dist.broadcast(self.header, src=0, group=self.group)

@@ -63,12 +63,20 @@ class Transcript:
 class Arena:
     """One HBM allocation, bump-allocated in Fr elements (MSM batches address scalars by offset)."""
 
-    def __init__(self, lib: Lib, elems: int):
+    def __init__(self, lib: Lib, elems: int, torch_device: str | None = None):
+        """`torch_device` ("cuda" / "cpu"): back the arena by a torch tensor so that slices can be used
+        in torch.distributed collectives (multi-GPU commit split); otherwise the library allocates."""
         self.lib = lib
         self.elems = elems
-        p = C.c_void_p()
-        lib.check(lib.c.apb_dev_alloc(elems * 32, C.byref(p)))
-        self.base = p.value
+        self.tensor = None
+        if torch_device is not None:
+            import torch
+            self.tensor = torch.zeros(elems * 4, dtype=torch.int64, device=torch_device)
+            self.base = self.tensor.data_ptr()
+        else:
+            p = C.c_void_p()
+            lib.check(lib.c.apb_dev_alloc(elems * 32, C.byref(p)))
+            self.base = p.value
         self.used = 0
 
     def alloc(self, elems: int) -> int:
@@ -97,8 +105,16 @@ class Arena:
         self.lib.check(self.lib.c.apb_dev_download(out.ctypes.data, self.ptr(off), elems * 32))
         return out
 
+    def view(self, off: int, elems: int):
+        """torch view (int64 words) of `elems` elements at element offset `off` (tensor-backed arenas)"""
+        return self.tensor[off * 4:(off + elems) * 4]
+
     def close(self):
-        if self.base:
+        if self.tensor is not None:
+            self.lib.c.apb_dev_sync()
+            self.tensor = None
+            self.base = 0
+        elif self.base:
             self.lib.c.apb_dev_free(self.base)
             self.base = 0
 
@@ -127,10 +143,15 @@ class ProverKey:
 
 
 class Prover:
-    def __init__(self, curve: int, ck: CommitterKey, lib: Lib | None = None):
+    def __init__(self, curve: int, ck: CommitterKey, lib: Lib | None = None, committer=None,
+                 arena_device: str | None = None):
+        """`committer`: optional parallel.DistributedCommitter that spreads the polynomials of each
+        PC::commit over the ranks of a process group (needs a tensor-backed arena: `arena_device`)."""
         self.lib = lib or get_lib()
         self.curve = curve
         self.ck = ck
+        self.committer = committer
+        self.arena_device = arena_device
         self.p = enc.FR_MODULUS[curve]
         self.msm_calls = 0
         self.ntt_calls = 0
@@ -149,6 +170,9 @@ class Prover:
         """PC::commit of device-resident polynomials -> list of (xyz, compressed bytes)"""
         k = len(offs)
         self.msm_calls += k
+        if self.committer is not None and self.committer.world > 1:
+            out = self.committer.commit(arena, offs, lens)
+            return [(out[i], self.lib.g1_compress(self.curve, out[i])) for i in range(k)]
         so = (C.c_size_t * k)(*offs)
         bo = (C.c_size_t * k)(*([0] * k))
         ln = (C.c_size_t * k)(*lens)
@@ -187,7 +211,8 @@ class Prover:
         sig_names = ["left_sigma", "right_sigma", "out_sigma", "fourth_sigma"]
         # residents: (8 selectors + 4 sigmas) polys + 4 tables + q_lookup evals + scratch ; 14 vectors of 4n
         # + the per-proof working set of `prove` (24 n-vectors, 11 4n-vectors, openings)
-        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 30) * n + (len(names) + 4 + 2 + 11) * 4 * n)
+        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 30) * n + (len(names) + 4 + 2 + 11) * 4 * n,
+                      torch_device=self.arena_device)
         pk = ProverKey(curve=curve, n=n, arena=arena, dom=dom, dom4=dom4)
         vals_mont = _mont_list(curve, circ.values)
         tmp = arena.alloc(n)

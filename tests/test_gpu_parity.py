@@ -91,3 +91,25 @@ def test_srs_from_tau_matches_oracle(gpu_lib):
         exp = enc.g1_affine_to_mont(curve, powers_of_tau_g1(CURVES[curve], 0xDEADBEEF12345, 300))
         assert (ck.download(0, 300) == exp).all()
         ck.close()
+
+
+def test_prover_2p18_verifies_under_restated_verifier(gpu_lib):
+    """BASELINE config #3 size: no oracle proof at 2^18 (minutes of Python), so the GPU proof is checked by the
+    restated reference verifier (oracle/plonk_verify.py) against the GPU-computed verifier key"""
+    from ark_plonk_b200 import bench_circuit as bc, kzg, plonk as gp
+    from oracle import plonk_verify as pv
+    from oracle.curves import BLS12_381
+    from oracle.serialize import deser_g1
+    tau, degree = 0x5EED5EED5EED5EED5EED1234567, 18
+    circ = bc.build(0, degree, [77 + i for i in range(8)])
+    ck = kzg.CommitterKey.from_tau(0, tau, circ.n + 1, lib=gpu_lib)
+    pr = gp.Prover(0, ck, lib=gpu_lib)
+    pk = pr.preprocess(circ, commit_verifier_key=True)
+    blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")
+    vk = {k: deser_g1(BLS12_381, v) for k, v in pk.commitments.items()}
+    assert pv.verify(BLS12_381, vk, circ.n, blob, tau)
+    bad = bytearray(blob)
+    bad[13 * 48 + 2 * 49 + 40] ^= 4
+    assert not pv.verify(BLS12_381, vk, circ.n, bytes(bad), tau)
+    pk.arena.close()
+    ck.close()

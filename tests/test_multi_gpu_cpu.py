@@ -63,3 +63,54 @@ def test_shard_bounds_cover_everything():
             cuts = [shard_bounds(n, world, r) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def _prove_worker(rank, world, port, emu_path, result_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["APB_MSM_C"] = "8"
+    os.environ["APB_NTT_MAX_LOG_TILE"] = "4"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hashlib
+    from ark_plonk_b200 import bench_circuit as bc, kzg, parallel, plonk as gp
+    from ark_plonk_b200._lib import Lib
+    import prover_cases
+    lib = Lib(emu_path)
+    lib.init()
+    case = prover_cases.golden_case(0, 5)
+    tau = int(case["tau"], 16)
+    circ = bc.build(0, 5, [int(b, 16) for b in case["blinders"]])
+    ck = kzg.CommitterKey.from_tau(0, tau, circ.n + 1, lib=lib)
+    com = parallel.DistributedCommitter(0, ck, circ.n, group=None, device="cpu", lib=lib)
+    ok, served = True, 0
+    if rank == 0:
+        pr = gp.Prover(0, ck, lib=lib, committer=com, arena_device="cpu")
+        pk = pr.preprocess(circ, commit_verifier_key=False)
+        blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")
+        ok = hashlib.sha256(blob).hexdigest() == case["proof_sha256"]
+        com.shutdown()
+    else:
+        served = com.serve()
+        ok = served == 6                      # the prover issues 6 batched commit calls per proof
+    result_q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_prove_with_commitments_split_over_two_ranks(emu_lib):
+    """batched prove: rank 0 proves, rank 1 serves half of the polynomials of every commit batch; the proof is
+    byte-identical to the golden vector"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_prove_worker, args=(r, 2, port, emu_lib.path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]

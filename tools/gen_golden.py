@@ -36,8 +36,10 @@ def main():
         pk = op.preprocess(cs, kz)
         cs2 = op.bench_circuit(cv, degree, bl)
         _, blob = op.prove(cs2, pk, kz, b"ark")
+        from oracle.serialize import ser_g1
+        vk = {k: ser_g1(cv, v).hex() for k, v in pk.commitments.items()}
         out.append({"curve": curve, "degree": degree, "tau": hex(tau), "blinders": [hex(b) for b in bl],
-                    "proof_sha256": hashlib.sha256(blob).hexdigest(), "proof": blob.hex()})
+                    "proof_sha256": hashlib.sha256(blob).hexdigest(), "proof": blob.hex(), "vk": vk})
         print(curve, degree, out[-1]["proof_sha256"], flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "plonk_proofs.json"), "w") as fh:
         json.dump(out, fh, indent=1)
