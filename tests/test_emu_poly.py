@@ -1,0 +1,21 @@
+"""Kernel-logic parity of the polynomial / prover kernels on the CPU emulation (small sizes)."""
+import parity_cases as pc
+import poly_cases
+
+
+def test_lincomb_eval_divide(emu_lib):
+    poly_cases.check_lincomb_eval_divide(emu_lib, 0, 300)
+    poly_cases.check_lincomb_eval_divide(emu_lib, 1, 37, seed=5)
+    poly_cases.check_lincomb_eval_divide(emu_lib, 0, 2100, seed=6)      # more than one 2048-coefficient eval block
+
+
+def test_combine_split_matches_reference_semantics(emu_lib):
+    poly_cases.check_combine_split(emu_lib, 0)
+    poly_cases.check_combine_split(emu_lib, 1, seed=8)
+
+
+def test_grand_products(emu_lib):
+    with pc.env(APB_NTT_MAX_LOG_TILE=4):
+        poly_cases.check_grand_products(emu_lib, 0, 5)
+        poly_cases.check_grand_products(emu_lib, 1, 4, seed=4)
+        poly_cases.check_grand_products(emu_lib, 0, 11, seed=7)         # several scan blocks

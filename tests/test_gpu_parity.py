@@ -113,3 +113,21 @@ def test_prover_2p18_verifies_under_restated_verifier(gpu_lib):
     assert not pv.verify(BLS12_381, vk, circ.n, bytes(bad), tau)
     pk.arena.close()
     ck.close()
+
+
+# ---- polynomial / prover kernels, unit parity -------------------------------------------------
+import poly_cases  # noqa: E402
+
+
+def test_poly_lincomb_eval_divide(gpu_lib):
+    poly_cases.check_lincomb_eval_divide(gpu_lib, 0, 5000)
+    poly_cases.check_lincomb_eval_divide(gpu_lib, 1, 1 << 12, seed=9)
+
+
+def test_poly_combine_split(gpu_lib):
+    poly_cases.check_combine_split(gpu_lib, 0)
+
+
+def test_poly_grand_products(gpu_lib):
+    poly_cases.check_grand_products(gpu_lib, 0, 12)
+    poly_cases.check_grand_products(gpu_lib, 1, 10, seed=11)
