@@ -12,6 +12,7 @@ std::atomic<uint64_t> g_launches{0};
 cudaStream_t g_stream = nullptr;
 bool g_inited = false;
 double g_last_ms = 0.0;
+std::recursive_mutex g_api_mutex;
 extern int g_num_sms;
 
 int set_err(int code, const char* fmt, ...) {
@@ -180,6 +181,7 @@ static int run_mul_bench28(int threads, int blocks_per_sm, int ilp, uint32_t ite
 }
 
 extern "C" int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
+    APB_API_LOCK();
     APB_REQUIRE_INIT();
     if (!muls_per_s) return set_err(APB_ERR_INVALID_ARG, "apb_mul_bench: null out");
     if (field == 4) return run_mul_bench28(threads, blocks_per_sm, ilp, iters, muls_per_s);
@@ -192,6 +194,7 @@ extern "C" int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp,
 }
 
 extern "C" int apb_init(int device) {
+    APB_API_LOCK();
     if (g_inited) return APB_OK;
 #ifndef APB_EMU
     int count = 0;
@@ -227,6 +230,7 @@ extern "C" double apb_last_device_ms(void) { return g_last_ms; }
 extern "C" void* apb_stream(void) { return (void*)g_stream; }
 
 extern "C" int apb_dev_alloc(size_t bytes, void** d_ptr) {
+    APB_API_LOCK();
     if (!d_ptr) return set_err(APB_ERR_INVALID_ARG, "apb_dev_alloc: null out");
     APB_REQUIRE_INIT();
     cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
@@ -234,28 +238,33 @@ extern "C" int apb_dev_alloc(size_t bytes, void** d_ptr) {
     return APB_OK;
 }
 extern "C" int apb_dev_free(void* d_ptr) {
+    APB_API_LOCK();
     if (d_ptr) APB_CUDA_TRY(cudaFree(d_ptr));
     return APB_OK;
 }
 extern "C" int apb_dev_upload(void* d_dst, const void* h_src, size_t bytes) {
+    APB_API_LOCK();
     APB_REQUIRE_INIT();
     APB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g_stream));
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
 }
 extern "C" int apb_dev_download(void* h_dst, const void* d_src, size_t bytes) {
+    APB_API_LOCK();
     APB_REQUIRE_INIT();
     APB_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g_stream));
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
 }
 extern "C" int apb_dev_sync(void) {
+    APB_API_LOCK();
     APB_REQUIRE_INIT();
     APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
 }
 
 extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count) {
+    APB_API_LOCK();
     if (field < 0 || field > 3 || op < 0 || op > 4) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: bad field/op");
     if (!a || !out || (op <= 2 && !b)) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: null argument");
     if (count == 0) return APB_OK;
@@ -282,6 +291,7 @@ extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t
 }
 
 extern "C" int apb_imad_peak(double* wide_per_s, double* imad32_per_s) {
+    APB_API_LOCK();
     APB_REQUIRE_INIT();
     uint32_t* d_out = nullptr;
     APB_CUDA_TRY(cudaMalloc((void**)&d_out, 64));

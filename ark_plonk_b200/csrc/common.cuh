@@ -1,6 +1,7 @@
 // Library-wide state: error reporting, the per-process stream, launch accounting.
 #pragma once
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string>
@@ -16,6 +17,7 @@ extern std::atomic<uint64_t> g_launches;
 extern cudaStream_t g_stream;
 extern bool g_inited;
 extern double g_last_ms;
+extern std::recursive_mutex g_api_mutex;   // the library has one stream and shared workspaces: entry points serialise
 
 int set_err(int code, const char* fmt, ...);
 
@@ -32,6 +34,8 @@ int set_err(int code, const char* fmt, ...);
         apb::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
         APB_LAUNCH(kernel, grid, block, smem, apb::g_stream, __VA_ARGS__);                  \
     } while (0)
+
+#define APB_API_LOCK() std::lock_guard<std::recursive_mutex> apb_api_lock_(apb::g_api_mutex)
 
 #define APB_CHECK_LAUNCH() APB_CUDA_TRY(cudaGetLastError())
 

@@ -380,28 +380,35 @@ struct TreeJob {
 };
 
 template <class FQ>
-__global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, const TreeJob* jobs) {
-    __shared__ uint4 sm[128 * 12];       // 128 XYZZ points (4 * 48 bytes)
-    const TreeJob J = jobs[blockIdx.x];
-    const uint32_t tid = threadIdx.x;
+__global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, const TreeJob* jobs, uint32_t njobs) {
+    // one job per warp (4 per CTA): every lane first folds m/32 strided elements sequentially, then
+    // a 5-level tree inside the warp through shared memory.  13 dependent additions for a
+    // 256-element job with 61 % of the lanes busy (the former CTA-wide tree: 9 deep but 22 %).
+    __shared__ uint4 sm[128 * 12];       // 128 XYZZ points (4 * 48 bytes), 32 per warp
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t job = blockIdx.x * 4 + (tid >> 5);
+    const bool active = job < njobs;
+    TreeJob J;
+    if (active) J = jobs[job];
+    else { J.base = 0; J.stride = 0; J.m = 0; J.woff = 0; J.selbit = -1; J.out = 0; }
     XYZZ<FQ> acc = XYZZ<FQ>::identity();
-    for (uint32_t e = tid; e < J.m; e += 128) {
+    for (uint32_t e = lane; e < J.m; e += 32) {
         if (J.selbit >= 0 && !(((e + J.woff) >> J.selbit) & 1)) continue;
         XYZZ<FQ> p = load_xyzz<FQ>(in, (uint64_t)J.base + (uint64_t)e * J.stride);
         acc.add(p);
     }
     store_xyzz<FQ>(sm, tid, acc);
     __syncthreads();
-    for (uint32_t s = 64; s >= 1; s >>= 1) {
-        if (tid < s) {
+    for (uint32_t s = 16; s >= 1; s >>= 1) {
+        if (lane < s) {
             XYZZ<FQ> p = load_xyzz<FQ>(sm, tid + s);
             acc.add(p);
         }
         __syncthreads();
-        if (tid < s) store_xyzz<FQ>(sm, tid, acc);
+        if (lane < s) store_xyzz<FQ>(sm, tid, acc);
         __syncthreads();
     }
-    if (tid == 0) store_xyzz<FQ>(out, J.out, acc);
+    if (active && lane == 0) store_xyzz<FQ>(out, J.out, acc);
 }
 
 // a^(p-2)
@@ -591,6 +598,7 @@ static int ck_precompute(apb_ck_s* ck) {
 // kept resident (the reference samples tau from OsRng: benches/plonk.rs:98, PC::setup).
 // generator_xy: 12 u64 affine generator (Montgomery); tau: 4 u64 Montgomery.
 extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const uint64_t* tau, size_t n, apb_ck_t* out) {
+    APB_API_LOCK();
     if (!out || !generator_xy || !tau) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: null argument");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: bad curve %d", curve);
     APB_REQUIRE_INIT();
@@ -627,6 +635,7 @@ extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const ui
 
 // copies `count` resident powers starting at `first` to host memory (12 u64 each)
 extern "C" int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t* out_xy) {
+    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC || !out_xy) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_download: bad handle");
     if (first + count > ck->n) return set_err(APB_ERR_INVALID_ARG, "apb_ck_download: range exceeds key size");
     const char* src = (const char*)(ck->bases_orig ? ck->bases_orig : ck->bases);
@@ -636,6 +645,7 @@ extern "C" int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t
 }
 
 extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* out) {
+    APB_API_LOCK();
     if (!out || (!xy && n)) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: null argument");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: bad curve %d", curve);
     APB_REQUIRE_INIT();
@@ -651,6 +661,7 @@ extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* 
 }
 
 extern "C" int apb_ck_size(apb_ck_t ck, size_t* n) {
+    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_size: bad handle");
     *n = ck->n;
     return APB_OK;
@@ -832,8 +843,10 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
                 (const void*)ck->partials, (const int32_t*)ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[3], g_stream);
     // 6. bucket reduction trees
-    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_a, 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs);
-    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)njobs_b, 128, 0, (const void*)ck->stage_a, ck->stage_b, (const TreeJob*)(ck->jobs + njobs_a));
+    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)((njobs_a + 3) / 4), 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs,
+                (uint32_t)njobs_a);
+    APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)((njobs_b + 3) / 4), 128, 0, (const void*)ck->stage_a, ck->stage_b,
+                (const TreeJob*)(ck->jobs + njobs_a), (uint32_t)njobs_b);
     APB_CHECK_LAUNCH();
     if (g_profile) cudaEventRecord(ev[4], g_stream);
     APB_CUDA_TRY(cudaMemcpyAsync(ck->h_out, ck->stage_b, out_bytes, cudaMemcpyDeviceToHost, g_stream));
@@ -893,6 +906,7 @@ static int msm_dispatch(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, 
 
 extern "C" int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scalars, const size_t* base_offsets,
                              const size_t* lens, int mont, uint64_t* out_xyz) {
+    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm: bad key handle");
     if (k == 0) return APB_OK;
     if (!scalars || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm: null argument");
@@ -922,12 +936,14 @@ extern "C" int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scala
 }
 
 extern "C" int apb_msm(apb_ck_t ck, size_t base_offset, const uint64_t* scalars, size_t n, int mont, uint64_t out_xyz[18]) {
+    APB_API_LOCK();
     const uint64_t* sp[1] = {scalars};
     size_t off[1] = {base_offset}, len[1] = {n};
     return apb_msm_batch(ck, 1, sp, off, len, mont, out_xyz);
 }
 
 extern "C" int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalars, size_t n, int mont, uint64_t out_xyz[18]) {
+    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_dev: bad key handle");
     if (!out_xyz || (n && !d_scalars)) return set_err(APB_ERR_INVALID_ARG, "apb_msm_dev: null argument");
     if (base_offset + n > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm_dev: %zu scalars at base offset %zu exceed the %zu resident powers", n, base_offset, ck->n);
@@ -942,6 +958,7 @@ extern "C" int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalar
 // d_scalars: one device buffer; scal_offs in elements
 extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t* scal_offs, const size_t* base_offsets,
                                  const size_t* lens, int mont, uint64_t* out_xyz) {
+    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_batch_dev: bad key handle");
     if (k == 0) return APB_OK;
     if (!d_scalars || !scal_offs || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm_batch_dev: null argument");
@@ -971,6 +988,7 @@ extern "C" void apb_msm_totals(double* accumulate_ms, unsigned long long* points
 
 // host-side group addition of two normalised / Jacobian points (folding per-GPU partial sums)
 extern "C" int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_xyz[18], uint64_t out_xyz[18]) {
+    APB_API_LOCK();
     if (!a_xyz || !b_xyz || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_g1_add: null argument");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_g1_add: bad curve");
     host::Group grp;
@@ -999,6 +1017,7 @@ extern "C" void apb_msm_phase_ms(double out[4]) {
 }
 
 extern "C" int apb_g1_compress(int curve, const uint64_t xyz[18], uint8_t out[48]) {
+    APB_API_LOCK();
     if (!xyz || !out) return set_err(APB_ERR_INVALID_ARG, "apb_g1_compress: null argument");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_g1_compress: bad curve");
     host::Field f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fq381>() : host::Field::make<Fq377>();

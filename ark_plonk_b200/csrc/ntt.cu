@@ -170,6 +170,7 @@ struct apb_domain_s {
     void *clo, *chi, *iclo, *ichi;        // coset tables
     void* scratch;
     size_t scratch_elems;
+    void *io_in, *io_out;                 // staging for the host-buffer entry point (apb_ntt)
     uint32_t size_inv[8];
     int npass;
     uint32_t lbits[3];
@@ -254,6 +255,7 @@ static void plan_passes(apb_domain_s* d) {
 }
 
 extern "C" int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out) {
+    APB_API_LOCK();
     if (!out) return set_err(APB_ERR_INVALID_ARG, "apb_domain_new: null out");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_domain_new: bad curve %d", curve);
     uint32_t adicity = curve == APB_CURVE_BLS12_381 ? (uint32_t)Fr381::TWO_ADICITY : (uint32_t)Fr377::TWO_ADICITY;
@@ -273,6 +275,7 @@ extern "C" int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out) {
 }
 
 extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
+    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_domain_size: bad handle");
     *n = d->n;
     return APB_OK;
@@ -280,6 +283,7 @@ extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
 
 // internal: lets the polynomial kernels reach the resident root table w^i, i < N/2
 extern "C" int apb_domain_info(apb_domain_t d, int* curve, uint32_t* log_n, const void** tw) {
+    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "bad domain handle");
     *curve = d->curve;
     *log_n = d->log_n;
@@ -291,6 +295,7 @@ extern "C" void apb_domain_free(apb_domain_t d) {
     if (!d || d->magic != DOMAIN_MAGIC) return;
     cudaFree(d->tw); cudaFree(d->itw); cudaFree(d->clo); cudaFree(d->chi);
     cudaFree(d->iclo); cudaFree(d->ichi); cudaFree(d->scratch);
+    cudaFree(d->io_in); cudaFree(d->io_out);
     d->magic = 0;
     delete d;
 }
@@ -384,6 +389,7 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
 
 extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, size_t in_stride, void* d_out,
                                  size_t out_stride, size_t batch, int sync) {
+    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
     if (kind < 0 || kind > 3) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: bad kind %d", kind);
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
@@ -398,17 +404,21 @@ extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, siz
 }
 
 extern "C" int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void* d_out, int sync) {
+    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
     return apb_ntt_batch_dev(d, kind, d_in, in_len, d->n, d_out, d->n, 1, sync);
 }
 
 extern "C" int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_len, uint64_t* out) {
+    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
     if (!out || (!in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
-    void *d_in = nullptr, *d_out = nullptr;
-    APB_CUDA_TRY(cudaMalloc(&d_in, (in_len ? in_len : 1) * 32));
-    APB_CUDA_TRY(cudaMalloc(&d_out, d->n * 32));
+    if (!d->io_in) {
+        APB_CUDA_TRY(cudaMalloc(&d->io_in, d->n * 32));
+        APB_CUDA_TRY(cudaMalloc(&d->io_out, d->n * 32));
+    }
+    void *d_in = d->io_in, *d_out = d->io_out;
     if (in_len) APB_CUDA_TRY(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, g_stream));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -424,7 +434,5 @@ extern "C" int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_l
         g_last_ms = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_in);
-    cudaFree(d_out);
     return rc;
 }

@@ -470,6 +470,7 @@ static bool bad_curve(int c) { return c != APB_CURVE_BLS12_381 && c != APB_CURVE
 
 extern "C" int apb_fr_lincomb(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* scalars,
                               void* d_out, size_t out_len) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_fr_lincomb: bad curve");
     if (!d_out || (k && (!d_polys || !lens || !scalars))) return set_err(APB_ERR_INVALID_ARG, "apb_fr_lincomb: null argument");
     APB_REQUIRE_INIT();
@@ -542,6 +543,7 @@ extern "C" int apb_domain_info(apb_domain_t d, int* curve, uint32_t* log_n, cons
 
 extern "C" int apb_plonk_perm_z(apb_domain_t dom, const void* const* d_wires, const void* const* d_sigmas, const uint64_t* beta,
                                 const uint64_t* gamma, void* d_z) {
+    APB_API_LOCK();
     int curve; uint32_t log_n; const void* tw;
     int rc = apb_domain_info(dom, &curve, &log_n, &tw);
     if (rc != APB_OK) return rc;
@@ -572,6 +574,7 @@ extern "C" int apb_plonk_perm_z(apb_domain_t dom, const void* const* d_wires, co
 
 extern "C" int apb_plonk_lookup_z2(apb_domain_t dom, const void* d_f, const void* d_t, const void* d_h1, const void* d_h2,
                                    const uint64_t* delta, const uint64_t* epsilon, void* d_z2) {
+    APB_API_LOCK();
     int curve; uint32_t log_n; const void* tw;
     int rc = apb_domain_info(dom, &curve, &log_n, &tw);
     if (rc != APB_OK) return rc;
@@ -592,6 +595,7 @@ extern "C" int apb_plonk_lookup_z2(apb_domain_t dom, const void* d_f, const void
 
 extern "C" int apb_plonk_lookup_f(int curve, const void* q_lookup, const void* wl, const void* wr, const void* wo, const void* w4,
                                   const void* t_comp, const uint64_t* zeta, void* d_out, size_t n) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_lookup_f: bad curve");
     if (!q_lookup || !wl || !wr || !wo || !w4 || !t_comp || !zeta || !d_out) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_lookup_f: null argument");
     APB_REQUIRE_INIT();
@@ -602,6 +606,7 @@ extern "C" int apb_plonk_lookup_f(int curve, const void* q_lookup, const void* w
 }
 
 extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d_f, size_t n, void* d_h1, void* d_h2) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_combine_split: bad curve");
     if (!d_t || !d_f || !d_h1 || !d_h2) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_combine_split: null argument");
     APB_REQUIRE_INIT();
@@ -647,6 +652,7 @@ extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d
 // args mirror struct QuotientArgs; passed as a flat table of 25 pointers + 10 scalars + 4 inverse values
 extern "C" int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* scalars10, const uint64_t* vh_inv4, void* d_out,
                                   size_t n4) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: bad curve");
     if (!ptrs25 || !scalars10 || !vh_inv4 || !d_out) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null argument");
     APB_REQUIRE_INIT();
@@ -741,6 +747,7 @@ static int poly_eval_impl(size_t k, const void* const* d_polys, const size_t* le
 
 extern "C" int apb_poly_eval(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* points,
                              uint64_t* out_vals) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_poly_eval: bad curve");
     if (k == 0) return APB_OK;
     if (!d_polys || !lens || !points || !out_vals) return set_err(APB_ERR_INVALID_ARG, "apb_poly_eval: null argument");
@@ -789,6 +796,7 @@ static int divide_impl(const void* d_p, size_t len, const uint64_t* z, void* d_o
 }
 
 extern "C" int apb_poly_divide_linear(int curve, const void* d_p, size_t len, const uint64_t* z, void* d_out) {
+    APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_poly_divide_linear: bad curve");
     if (!z || (len > 1 && (!d_p || !d_out))) return set_err(APB_ERR_INVALID_ARG, "apb_poly_divide_linear: null argument");
     APB_REQUIRE_INIT();
