@@ -40,11 +40,6 @@ unsigned long long g_points_total = 0;  // scalars processed while profiling
 double g_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sort, accumulate, stitch, trees, copy+host epilogue
 
 static const int MAX_BATCH = 16;
-#ifdef APB_EMU
-static const int SCAN_THREADS = 64;
-#else
-static const int SCAN_THREADS = 1024;
-#endif
 static const int MAX_COPIES = 16;
 
 struct MsmBatch {
@@ -141,31 +136,6 @@ __global__ void k_msm_digits(const void* scalars, MsmBatch B, MsmGeom g, int mon
             entries[pos] = (uint32_t)pidx | (neg ? 0x80000000u : 0u);
         }
     }
-}
-
-// exclusive scan of counts[0..n) into offsets[0..n], single CTA (n is at most a few 100k)
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive(const uint32_t* counts, uint32_t* offsets, uint32_t n) {
-    __shared__ uint32_t part[1024];
-    const uint32_t tid = threadIdx.x, nth = blockDim.x;
-    const uint32_t per = (n + nth - 1) / nth;
-    const uint32_t lo = tid * per, hi = lo + per < n ? lo + per : n;
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    part[tid] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread sums
-    for (uint32_t off = 1; off < nth; off <<= 1) {
-        uint32_t v = tid >= off ? part[tid - off] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    uint32_t run = tid ? part[tid - 1] : 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        offsets[i] = run;
-        run += counts[i];
-    }
-    if (tid == nth - 1) offsets[n] = part[nth - 1];
 }
 
 template <class FQ>
@@ -742,16 +712,14 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
 
     // chunk size for the accumulate pass: exactly one resident wave of threads
-    static int acc_variant = -1, resident_blocks[2] = {2, 3};
+    static int acc_variant = -1, resident_blocks[1] = {2};
     if (acc_variant < 0) {
         acc_variant = 0;
-        if (const char* e = getenv("APB_MSM_ACC_VARIANT")) acc_variant = atoi(e) ? 1 : 0;
 #ifndef APB_EMU
         int nb = 0;
         if (ck->radix == 28) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate28<typename CV::FQ28, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
         } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 3>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
 #endif
     }
     uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[acc_variant] * 128;
@@ -828,15 +796,11 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     typedef typename CV::FQ28 FQ28;
     auto k_acc28 = k_msm_accumulate28<FQ28, 2>;
     auto k_acc2 = k_msm_accumulate<FQ, 2>;
-    auto k_acc3 = k_msm_accumulate<FQ, 3>;
     if (ck->radix == 28)
         APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                     (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
-    else if (acc_variant == 0)
-        APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
-                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     else
-        APB_KLAUNCH(k_acc3, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+        APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                     (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[2], g_stream);
     APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
