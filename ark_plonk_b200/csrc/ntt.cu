@@ -243,7 +243,9 @@ static int build_tables(apb_domain_s* d) {
 }
 
 static void plan_passes(apb_domain_s* d) {
-    int maxbits = 10;
+    // measured on B200 (tools/ntt_tune.py, profiles/r01_ntt_tune.txt): three passes of <= 2^8-point tiles
+    // beat two passes of 2^10-point tiles by ~10 % (fewer barrier-separated stages per tile, more CTAs/SM)
+    int maxbits = 8;
     if (const char* e = getenv("APB_NTT_MAX_LOG_TILE")) maxbits = atoi(e);
     if (maxbits < 1) maxbits = 1;
     if (maxbits > 10) maxbits = 10;
@@ -306,7 +308,7 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
     const bool inverse = kind == APB_NTT_IFFT || kind == APB_NTT_COSET_IFFT;
     const uint32_t L = d->log_n;
     const int P = d->npass;
-    int log_cols_max = 4;
+    int log_cols_max = 1;
     if (const char* e = getenv("APB_NTT_LOG_COLS")) log_cols_max = atoi(e);
     if (P > 1 && d->scratch_elems < d->n * batch) {
         cudaFree(d->scratch);

@@ -78,7 +78,7 @@ class DistributedCommitter:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.header = torch.zeros(2 + k_max, dtype=torch.int64, device=device)
         self.stage = torch.zeros(k_max * n_max * 4, dtype=torch.int64, device=device)
-        self.results = torch.zeros(k_max * 18, dtype=torch.int64, device=device)
+        self.results = torch.zeros(k_max * max(self.world, 1) * 18, dtype=torch.int64, device=device)
         self._stream = None
         if device == "cuda":
             self._stream = torch.cuda.ExternalStream(self.lib.c.apb_stream())
@@ -87,21 +87,38 @@ class DistributedCommitter:
         import contextlib
         return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
 
-    def _local_msms(self, k: int, lens) -> None:
-        """MSMs of the staged polynomials owned by this rank -> self.results rows (others zero)"""
+    def _tasks(self, k: int, lens):
+        """work of this rank for a batch of k polynomials: [(poly j, lo, hi, result slot)], slices per poly S.
+        k >= world: whole polynomials round-robin; k < world: every polynomial is cut into world // k
+        contiguous coefficient ranges (point split inside the polynomial split)"""
+        W, r = self.world, self.rank
+        if k >= W:
+            return [(j, 0, int(lens[j]), j) for j in range(k) if j % W == r], 1
+        S = W // k
+        if r >= k * S:
+            return [], S
+        j, sidx = r % k, r // k
+        per = (int(lens[j]) + S - 1) // S
+        lo = min(sidx * per, int(lens[j]))
+        hi = min(lo + per, int(lens[j]))
+        return ([(j, lo, hi, j * S + sidx)] if hi > lo else []), S
+
+    def _local_msms(self, k: int, lens) -> int:
+        """MSMs of this rank's share of the staged polynomials -> self.results slots (others zero)"""
         import ctypes as C
-        mine = [j for j in range(k) if j % self.world == self.rank]
+        tasks, S = self._tasks(k, lens)
         self.results.zero_()
-        if mine:
-            m = len(mine)
-            so = (C.c_size_t * m)(*[j * self.n for j in mine])
-            bo = (C.c_size_t * m)(*([0] * m))
-            ln = (C.c_size_t * m)(*[int(lens[j]) for j in mine])
+        if tasks:
+            m = len(tasks)
+            so = (C.c_size_t * m)(*[j * self.n + lo for j, lo, _, _ in tasks])
+            bo = (C.c_size_t * m)(*[lo for _, lo, _, _ in tasks])
+            ln = (C.c_size_t * m)(*[hi - lo for _, lo, hi, _ in tasks])
             out = np.zeros((m, 18), dtype=np.uint64)
             self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, m, self.stage.data_ptr(), so, bo, ln, 1, out.ctypes.data))
             host = torch.from_numpy(out.view(np.int64))
-            for i, j in enumerate(mine):
-                self.results[j * 18:(j + 1) * 18].copy_(host[i])
+            for i, (_, _, _, slot) in enumerate(tasks):
+                self.results[slot * 18:(slot + 1) * 18].copy_(host[i])
+        return S
 
     def commit(self, arena, offs, lens) -> np.ndarray:
         """rank 0: commitments of the k polynomials at arena offsets `offs` -> (k, 18) uint64"""
@@ -118,9 +135,14 @@ class DistributedCommitter:
                 dist.broadcast(self.stage[: kk * self.n * 4], src=0, group=self.group)
                 if self._stream is not None:
                     self._stream.synchronize()
-                self._local_msms(kk, lens[base:base + kk])
+                S = self._local_msms(kk, lens[base:base + kk])
                 dist.all_reduce(self.results, group=self.group)
-                out[base:base + kk] = self.results[: kk * 18].cpu().numpy().view(np.uint64).reshape(kk, 18)
+                parts = self.results[: kk * S * 18].cpu().numpy().view(np.uint64).reshape(kk, S, 18)
+                for j in range(kk):
+                    acc = parts[j, 0]
+                    for sidx in range(1, S):               # fold the point slices of polynomial j (host, 144-byte points)
+                        acc = self.lib.g1_add(self.curve, acc, parts[j, sidx])
+                    out[base + j] = acc
         return out
 
     def serve(self) -> int:

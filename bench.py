@@ -92,6 +92,27 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic(kernel_prefix: str):
+    """average DRAM bytes per launch of a kernel from the committed ncu capture (profiles/), or None"""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_prove_kernels.json")))
+    except Exception:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, cnt = 0.0, 0
+    for r in rows:
+        if kernel_prefix not in r.get("Kernel Name", ""):
+            continue
+        b = 0.0
+        for k, v in r.items():
+            if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+                unit = k[k.index("[") + 1:-1] if "[" in k else "byte"
+                b += float(v) * scale.get(unit, 1.0)
+        tot += b
+        cnt += 1
+    return tot / cnt if cnt else None
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -365,7 +386,9 @@ def run_b200(args):
                        "vs_baseline_note": "this value / published 20184 ms (Ryzen 7 3700X CPU, reference README.md:107); < 1 is faster"},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": len(proof) + 29 * 3024},
             "roofline": {"kernel": "k_msm_accumulate", "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
-                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": None,
+                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": ncu_traffic("k_msm_accumulate"),
+                         "traffic_note": "DRAM bytes per launch, mean of the 6 launches of one proof, ncu --set full (profiles/r01_ncu_prove_kernels.json); "
+                                         "algorithmic bytes per launch = entries x (4 B id + 96 B point) = %.2e" % (pts_total / K * 16 * 100 / 6),
                          "kernel_ms_per_launch": acc_per_launch, "launches_per_step": 6,
                          "kernel_share_of_step": acc_total_ms / K / ms_per_step,
                          "peak_source": "measured live: independent mad.wide.u32 chains (apb_imad_peak)",

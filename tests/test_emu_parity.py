@@ -72,3 +72,26 @@ def test_msm_empty_and_errors(emu_lib):
         kzg.commit(ck, [enc.fr_to_mont(0, [1, 2, 3, 4, 5])])
     assert ei.value.code == 2                                   # TooManyCoefficients
     ck.close()
+
+
+def test_error_behaviour(emu_lib):
+    """status codes mirror the reference's errors: Error::InvalidEvalDomainSize (prover.rs:169-173),
+    TooManyCoefficients (kzg10 degree check), plus argument validation; messages are thread-local"""
+    import ctypes as C
+    import numpy as np
+    from ark_plonk_b200 import ApbError, Radix2EvaluationDomain
+    with pytest.raises(ApbError) as ei:
+        Radix2EvaluationDomain(0, 1 << 33, lib=emu_lib)          # log_n 33 > two-adicity 32 of BLS12-381 Fr
+    assert ei.value.code == 3
+    h = C.c_void_p()
+    assert emu_lib.c.apb_domain_new(7, 4, C.byref(h)) == 1          # bad curve id
+    d = Radix2EvaluationDomain(0, 8, lib=emu_lib)
+    with pytest.raises(ApbError) as ei:
+        d.fft(np.zeros((9, 4), dtype=np.uint64))                    # more coefficients than the domain holds
+    assert ei.value.code == 1
+    out = np.zeros((8, 4), dtype=np.uint64)
+    assert emu_lib.c.apb_ntt(None, 0, None, 0, out.ctypes.data) == 4 and b"handle" in emu_lib.c.apb_last_error()
+    assert emu_lib.c.apb_ntt(d._h, 9, None, 0, out.ctypes.data) == 1  # bad transform kind
+    z = d.fft(np.zeros((0, 4), dtype=np.uint64))                    # empty polynomial -> N zeros (coset_fft of q_range etc.)
+    assert z.shape == (8, 4) and not z.any()
+    d.close()

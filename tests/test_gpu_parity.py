@@ -72,7 +72,7 @@ def test_msm_windowed_geometry(gpu_lib):
 import prover_cases  # noqa: E402
 
 
-@pytest.mark.parametrize("curve,degree", [(0, 5), (0, 8), (0, 10), (1, 6), (0, 12), (0, 14), (0, 16)])
+@pytest.mark.parametrize("curve,degree", [(0, 5), (0, 8), (0, 10), (1, 6), (1, 10), (0, 12), (0, 14), (0, 16)])
 def test_prover_byte_identical_to_oracle(gpu_lib, curve, degree):
     """BASELINE configs #1 (2^10) and #2 (2^16): the serialized Proof equals the oracle's golden vector"""
     prover_cases.prove_case(gpu_lib, prover_cases.golden_case(curve, degree), repeat=2)

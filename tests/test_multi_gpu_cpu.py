@@ -114,3 +114,57 @@ def test_prove_with_commitments_split_over_two_ranks(emu_lib):
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def _commit_split_worker(rank, world, port, emu_path, result_q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["APB_MSM_C"] = "8"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from ark_plonk_b200 import encoding as enc, kzg, parallel, synth
+    from ark_plonk_b200._lib import Lib
+    from ark_plonk_b200.plonk import Arena
+    lib = Lib(emu_path)
+    lib.init()
+    n = 29
+    pts = synth.progression_bases(0, 3, 7, n)
+    ck = kzg.CommitterKey(0, enc.g1_affine_to_mont(0, pts), lib=lib)
+    com = parallel.DistributedCommitter(0, ck, n, k_max=4, device="cpu", lib=lib)
+    ok = True
+    if rank == 0:
+        arena = Arena(lib, 8 * n, torch_device="cpu")
+        rnd = random.Random(5)
+        polys = [[rnd.randrange(enc.FR_MODULUS[0]) for _ in range(ln)] for ln in (n, n - 1, 7)]
+        offs = []
+        for q in polys:
+            o = arena.alloc(n)
+            arena.upload(o, enc.fr_to_mont(0, q))
+            offs.append(o)
+        # k = 1 < world: the single polynomial is point-split over both ranks; k = 3 >= world: round robin
+        for sel in ([0], [1], [0, 1, 2]):
+            out = com.commit(arena, [offs[i] for i in sel], [len(polys[i]) for i in sel])
+            for row, i in zip(out, sel):
+                ok = ok and enc.g1_from_xyz(0, row) == synth.progression_expected(0, 3, 7, polys[i])
+        com.shutdown()
+    else:
+        ok = com.serve() == 3
+    result_q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_commit_batches_point_split_when_fewer_polys_than_ranks(emu_lib):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_commit_split_worker, args=(r, 2, port, emu_lib.path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]

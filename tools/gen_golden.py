@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from oracle import plonk as op  # noqa: E402
 from oracle.curves import CURVES  # noqa: E402
 
-CASES = [(0, 5), (0, 8), (0, 10), (1, 6), (0, 12), (0, 14), (0, 16)]
+CASES = [(0, 5), (0, 8), (0, 10), (1, 6), (1, 10), (0, 12), (0, 14), (0, 16)]
 
 
 def seeded(curve, degree):
