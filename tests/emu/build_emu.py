@@ -19,6 +19,20 @@ SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "transcript.cu"]
 FLAGS = ["-std=c++20", "-O2", "-DAPB_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC, "-w"]
 
 
+def build_asan() -> str:
+    """AddressSanitizer variant (tools/emu_asan.sh): exact-size 'device' allocations, -fsanitize=address"""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libapb_emu_asan.so")
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(OUT, s.replace(".cu", ".asan.o"))
+        objs.append(obj)
+        subprocess.check_call(["g++", *FLAGS, "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-DAPB_EMU_ASAN",
+                               "-x", "c++", "-c", os.path.join(CSRC, s), "-o", obj])
+    subprocess.check_call(["g++", "-shared", "-pthread", "-fsanitize=address", "-o", lib, *objs])
+    return lib
+
+
 def build(force: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
@@ -45,4 +59,5 @@ def build(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build_asan() if "--asan" in sys.argv else build(force=True))
