@@ -193,7 +193,79 @@ struct Fp {
         reduce_once(r.v);
         return r;
     }
-    APB_HD Fp sqr() const { return *this * *this; }
+    // ---- Montgomery square (base fields only: needs 3p < 2^(32N)) ---------------------------
+    // CIOS where step i multiplies a_i by the vector [0,..,0, a_i, 2*a_{>i}]: every off-diagonal
+    // product a_i*a_j is formed once (N(N+1)/2 = 78 instead of 144 for N = 12).  2*a_{>i} is read
+    // limb-wise with funnel shifts: limb i+1 is a_{i+1} << 1, limb j > i+1 is (a_j << 1) | (a_{j-1} >> 31).
+    template <int I>
+    APB_HD static uint32_t sq_vec(const uint32_t* a, int j) {
+        return j == I ? a[j] : (j == I + 1 ? (a[j] << 1) : ((a[j] << 1) | (a[j - 1] >> 31)));
+    }
+    template <int I>
+    APB_HD static void cios_step_sq(uint32_t* E, uint32_t* O, const uint32_t* a) {
+        const uint32_t bi = a[I];
+        if (I == 0) {
+            _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+                const uint32_t ve = sq_vec<0>(a, j), vo = sq_vec<0>(a, j + 1);
+                E[j] = mul_lo(ve, bi);
+                E[j + 1] = mul_hi(ve, bi);
+                O[j] = mul_lo(vo, bi);
+                O[j + 1] = mul_hi(vo, bi);
+            }
+        } else {
+            E[0] = add_cc(E[0], O[1]);
+            _Pragma("unroll") for (int j = 1; j < N - 1; j += 2) {       // odd columns: shift O down by 2
+                if (j >= I) {
+                    const uint32_t v = sq_vec<I>(a, j);
+                    O[j - 1] = madc_lo_cc(v, bi, O[j + 1]);
+                    O[j] = madc_hi_cc(v, bi, O[j + 2]);
+                } else {
+                    O[j - 1] = addc_cc(O[j + 1], 0);
+                    O[j] = addc_cc(O[j + 2], 0);
+                }
+            }
+            {
+                const uint32_t v = sq_vec<I>(a, N - 1);                  // N-1 >= I always
+                O[N - 2] = madc_lo_cc(v, bi, 0);
+                O[N - 1] = madc_hi(v, bi, 0);
+            }
+            constexpr int J0 = (I + 1) & ~1;                             // first even column >= I
+            if (J0 < N) {
+                const uint32_t v0 = sq_vec<I>(a, J0);
+                E[J0] = mad_lo_cc(v0, bi, E[J0]);
+                E[J0 + 1] = madc_hi_cc(v0, bi, E[J0 + 1]);
+                _Pragma("unroll") for (int j = J0 + 2; j < N; j += 2) {
+                    const uint32_t v = sq_vec<I>(a, j);
+                    E[j] = madc_lo_cc(v, bi, E[j]);
+                    E[j + 1] = madc_hi_cc(v, bi, E[j + 1]);
+                }
+                O[N - 1] = addc(O[N - 1], 0);
+            }
+        }
+        uint32_t m = mul_lo(E[0], P::N0INV);
+        chain_mad_mod<1>(O, m);
+        chain_mad_mod<0>(E, m);
+        O[N - 1] = addc(O[N - 1], 0);
+    }
+    template <int I>
+    APB_HD static void sq_steps(uint32_t* X, uint32_t* Y, const uint32_t* a) {
+        if (I < N) {
+            if (I & 1) cios_step_sq<(I < N ? I : 0)>(Y, X, a);
+            else cios_step_sq<(I < N ? I : 0)>(X, Y, a);
+            sq_steps<(I < N ? I + 1 : N)>(X, Y, a);
+        }
+    }
+    APB_HD Fp sqr() const {
+        if (N != 12) return *this * *this;          // Fr: 3p does not fit 2^256 - use the generic product
+        uint32_t X[N], Y[N];
+        sq_steps<0>(X, Y, v);
+        Fp r;
+        r.v[0] = add_cc(X[0], Y[1]);
+        _Pragma("unroll") for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+        r.v[N - 1] = addc(X[N - 1], 0);
+        reduce_once(r.v);
+        return r;
+    }
 
     // a*R mod p  <-  a          /   a  <-  a*R mod p
     APB_HD Fp to_mont() const { return *this * r2(); }

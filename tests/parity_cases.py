@@ -44,6 +44,7 @@ def check_field_ops(lib, count=64, seed=1):
         assert enc.limbs_to_ints(lib.field_op(fid, 2, A, B)) == [(x - y) % f.p for x, y in zip(a, b)], f.name
         assert enc.limbs_to_ints(lib.field_op(fid, 3, A, None)) == [x * f.R % f.p for x in a], f.name
         assert enc.limbs_to_ints(lib.field_op(fid, 4, A, None)) == [x * rinv % f.p for x in a], f.name
+        assert enc.limbs_to_ints(lib.field_op(fid, 5, A, None)) == [x * x * rinv % f.p for x in a], f.name
 
 
 def check_ntt(lib, curve, log_n, in_len, seed=2, kinds=("fft", "ifft", "coset_fft", "coset_ifft")):
