@@ -104,6 +104,42 @@ def commit(ck: CommitterKey, polys):
     return [out[i] for i in range(k)]
 
 
+def open(ck: CommitterKey, polys, point: int, opening_challenge: int):
+    """`PC::open(ck, polys, _, &point, opening_challenge, _, None)` (sonic_pc): p = sum challenge^i p_i,
+    witness = p / (X - point) (remainder dropped), proof.w = commit(witness); random_v = None.
+    The combination, the division and the MSM run on the device.  Returns the normalised point record."""
+    from .plonk import Arena
+    lib, curve = ck.lib, ck.curve
+    p = enc.FR_MODULUS[curve]
+    polys = [np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 4) for q in polys]
+    m = max((q.shape[0] for q in polys), default=0)
+    out = np.zeros(18, dtype=np.uint64)
+    if m <= 1:
+        return out                                         # constant or zero polynomial: witness is zero
+    if m - 1 > ck.n:
+        raise ApbError(2, "witness polynomial of degree %d exceeds the %d supported powers" % (m - 2, ck.n))
+    arena = Arena(lib, (len(polys) + 2) * m + 8)
+    try:
+        offs = []
+        for q in polys:
+            o = arena.alloc(max(q.shape[0], 1))
+            if q.shape[0]:
+                arena.upload(o, q)
+            offs.append(o)
+        comb, wit = arena.alloc(m), arena.alloc(m)
+        k = len(polys)
+        ptrs = (C.c_void_p * k)(*[arena.ptr(o) for o in offs])
+        lens = (C.c_size_t * k)(*[q.shape[0] for q in polys])
+        sc = np.ascontiguousarray(enc.fr_to_mont(curve, [pow(opening_challenge, i, p) for i in range(k)]))
+        lib.check(lib.c.apb_fr_lincomb(curve, k, ptrs, lens, sc.ctypes.data, arena.ptr(comb), m))
+        z = np.ascontiguousarray(enc.fr_to_mont(curve, [point]))
+        lib.check(lib.c.apb_poly_divide_linear(curve, arena.ptr(comb), m, z.ctypes.data, arena.ptr(wit)))
+        lib.check(lib.c.apb_msm_dev(ck._h, 0, arena.ptr(wit), m - 1, 1, out.ctypes.data))
+    finally:
+        arena.close()
+    return out
+
+
 def compress(ck_or_curve, xyz: np.ndarray, lib: Lib | None = None) -> bytes:
     """ark-serialize compressed bytes of a commitment (what the transcript absorbs)."""
     if isinstance(ck_or_curve, CommitterKey):

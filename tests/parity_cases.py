@@ -182,3 +182,36 @@ def edge_scalars(curve, n):
     base = [0, 1, 2, r - 1, r - 2, (r - 1) // 2, (r + 1) // 2, 5, 0, 0, 0, 7, 1 << 200, (1 << 250) + 5, 12345,
             (1 << 16) - 1, 1 << 15, (1 << 15) + 1, (1 << 255) % r, r - (1 << 15)]
     return (base * (n // len(base) + 1))[:n]
+
+
+def check_kzg_open_and_domain_helpers(lib, curve, log_n, seed=12):
+    """PC::open against the oracle's sonic_pc restatement, and the EvaluationDomain helper calls"""
+    from oracle.plonk import Kzg
+    cv = CURVES[curve]
+    p = cv.fr.p
+    n = 1 << log_n
+    rnd = random.Random(seed)
+    tau = rnd.randrange(1, p)
+    ck = kzg.CommitterKey.from_tau(curve, tau, n, lib=lib)
+    try:
+        polys = [[rnd.randrange(p) for _ in range(ln)] for ln in (n, n - 3, 1, 0, n)]
+        z, ch = rnd.randrange(p), rnd.randrange(2, p)
+        got = kzg.open(ck, [enc.fr_to_mont(curve, q) for q in polys], z, ch)
+        exp, _ = Kzg(cv, tau, n).open(polys, z, ch)
+        assert enc.g1_from_xyz(curve, got) == exp
+    finally:
+        ck.close()
+    d = Radix2EvaluationDomain(curve, n, lib=lib)
+    try:
+        od = Domain(FR[curve], log_n)
+        assert d.group_gen() == od.group_gen and d.size_inv() == od.size_inv and d.element(3) == od.element(3)
+        assert enc.fr_from_mont(curve, d.elements()) == od.elements()
+        t = rnd.randrange(p)
+        assert d.evaluate_vanishing_polynomial(t) == od.evaluate_vanishing_polynomial(t)
+        lag = d.evaluate_all_lagrange_coefficients(t)
+        x = [rnd.randrange(p) for _ in range(n)]                     # sum_i L_i(t) f(w^i) == f(t) for deg f < n
+        evals = od.fft(x)
+        assert sum(l * e for l, e in zip(lag, evals)) % p == poly_eval(FR[curve], x, t)
+        assert d.evaluate_all_lagrange_coefficients(od.element(5 % n))[5 % n] == 1
+    finally:
+        d.close()

@@ -19,3 +19,9 @@ def test_grand_products(emu_lib):
         poly_cases.check_grand_products(emu_lib, 0, 5)
         poly_cases.check_grand_products(emu_lib, 1, 4, seed=4)
         poly_cases.check_grand_products(emu_lib, 0, 11, seed=7)         # several scan blocks
+
+
+def test_kzg_open_and_domain_helpers(emu_lib):
+    with pc.env(APB_MSM_C=8, APB_NTT_MAX_LOG_TILE=4):
+        pc.check_kzg_open_and_domain_helpers(emu_lib, 0, 5)
+        pc.check_kzg_open_and_domain_helpers(emu_lib, 1, 4, seed=13)

@@ -131,3 +131,8 @@ def test_poly_combine_split(gpu_lib):
 def test_poly_grand_products(gpu_lib):
     poly_cases.check_grand_products(gpu_lib, 0, 12)
     poly_cases.check_grand_products(gpu_lib, 1, 10, seed=11)
+
+
+def test_kzg_open_and_domain_helpers(gpu_lib):
+    pc.check_kzg_open_and_domain_helpers(gpu_lib, 0, 10)
+    pc.check_kzg_open_and_domain_helpers(gpu_lib, 1, 8, seed=14)
