@@ -317,6 +317,17 @@ def run_b200(args):
         pr = gp.Prover(0, ck, committer=committer, arena_device="cuda" if split else None)
         pk = pr.preprocess(circ, commit_verifier_key=False)
         if split:
+            import atexit
+            _released = []
+
+            def _release_workers():          # never leave the worker ranks blocked in a broadcast if rank 0 dies
+                if not _released:
+                    _released.append(1)
+                    try:
+                        committer.shutdown()
+                    except Exception:
+                        pass
+            atexit.register(_release_workers)
             barrier()
             _real_barrier, barrier = barrier, (lambda: torch.cuda.synchronize())    # workers are inside serve()
         wires = gp.wires_to_mont(circ)
@@ -362,7 +373,7 @@ def run_b200(args):
         no_dead_ms = (time.perf_counter() - t0) * 1e3 / max(K // 2, 1)
         assert proof_nd == proof
         if split:
-            committer.shutdown()
+            _release_workers()
             barrier = _real_barrier
             barrier()
             total_ms = max_over_ranks(total_ms)
