@@ -40,19 +40,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     procs = []
+    hdr = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if not f.endswith(".cu"):
+            hdr.update(f.encode() + open(os.path.join(CSRC, f), "rb").read())
+    hdr.update(open(os.path.join(HERE, "..", "include", "apb.h"), "rb").read() + " ".join(NVCC_FLAGS).encode())
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        ostamp = obj + ".stamp"
+        odig = hashlib.sha256(hdr.digest() + open(os.path.join(CSRC, src), "rb").read()).hexdigest()
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == odig:
+            continue                      # this translation unit and every header are unchanged
         cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, p in procs:
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), ostamp, odig))
+    for src, p, ostamp, odig in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
+        with open(ostamp, "w") as fh:
+            fh.write(odig)
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs])
     with open(stamp, "w") as fh:
         fh.write(dig)
