@@ -136,3 +136,41 @@ def test_poly_grand_products(gpu_lib):
 def test_kzg_open_and_domain_helpers(gpu_lib):
     pc.check_kzg_open_and_domain_helpers(gpu_lib, 0, 10)
     pc.check_kzg_open_and_domain_helpers(gpu_lib, 1, 8, seed=14)
+
+
+# ---- BASELINE sweep sizes (configs #4 / #5): size-independent checks at large N --------------------
+def test_msm_2p22_tau_identity(gpu_lib):
+    """2^22 powers of tau generated on the device; MSM == [sum s_i tau^i]G (one host scalar multiplication)"""
+    import numpy as np
+    import torch
+    from ark_plonk_b200 import encoding as enc, kzg, synth
+    n, tau = 1 << 22, 0xA5A5A5A5DEADBEEF0123456789
+    ck = kzg.CommitterKey.from_tau(0, tau, n, lib=gpu_lib)
+    S = synth.seeded_scalars(0, n, seed=b"2p22")
+    out = kzg.multi_scalar_mul(ck, S)
+    r = enc.FR_MODULUS[0]
+    e, tp = 0, 1
+    for s in synth.limbs_to_int_list(S):
+        e = (e + s * tp) % r
+        tp = tp * tau % r
+    assert enc.g1_from_xyz(0, out) == synth.scalar_mul(0, synth.G1_GENERATOR[0], e)
+    ck.close()
+
+
+@pytest.mark.parametrize("log_n", [26, 28])
+def test_ntt_roundtrip_on_device_large(gpu_lib, log_n):
+    """coset_ifft(coset_fft(x)) == x and ifft(fft(x)) == x for a single large transform resident in HBM"""
+    import torch
+    from ark_plonk_b200.domain import Radix2EvaluationDomain
+    n = 1 << log_n
+    d = Radix2EvaluationDomain(0, n, lib=gpu_lib)
+    x = torch.randint(0, 2 ** 60, (n, 4), dtype=torch.int64, device="cuda")
+    y = torch.empty_like(x)
+    for fwd, inv in ((2, 3), (0, 1)):
+        d.ntt_dev(fwd, x.data_ptr(), n, y.data_ptr(), sync=True)
+        assert not torch.equal(x[:1024], y[:1024])
+        d.ntt_dev(inv, y.data_ptr(), n, y.data_ptr(), sync=True)
+        assert torch.equal(x, y)
+    d.close()
+    del x, y
+    torch.cuda.empty_cache()
