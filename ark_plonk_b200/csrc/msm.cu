@@ -712,9 +712,9 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
 
     // chunk size for the accumulate pass: exactly one resident wave of threads
-    static int acc_variant = -1, resident_blocks[1] = {2};
-    if (acc_variant < 0) {
-        acc_variant = 0;
+    static int occupancy_known = 0, resident_blocks[1] = {2};
+    if (!occupancy_known) {
+        occupancy_known = 1;
 #ifndef APB_EMU
         int nb = 0;
         if (ck->radix == 28) {
@@ -722,7 +722,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
 #endif
     }
-    uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[acc_variant] * 128;
+    uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[0] * 128;
     uint32_t E = (uint32_t)((Mmax + target_threads - 1) / target_threads);
     if (E < 8) E = 8;
     if (const char* e = getenv("APB_MSM_CHUNK")) E = (uint32_t)atoi(e);

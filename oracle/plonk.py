@@ -522,31 +522,3 @@ def serialize_proof(curve: Curve, proof) -> bytes:
     for lab, v in proof["custom_evals"]:
         out += ser_string(lab) + ser_field(curve.fr, v)
     return out
-
-
-# --------------------------------------------------------------------------------------------
-# acceptance check with known tau: the KZG opening equations in discrete-log form
-# --------------------------------------------------------------------------------------------
-def check_openings(cs: Composer, pk: ProverKey, kzg: Kzg, proof, trace) -> bool:
-    """w(tau) * (tau - z) == p(tau) - p(z) for both aggregated openings, with p rebuilt from the
-    proof's commitments' pre-images (the oracle knows the polynomials) - the prover-side identity
-    PC::check would verify with pairings (proof.rs:398-425)."""
-    p = cs.p
-    f = cs.curve.fr
-    tau = kzg.tau
-    zc = trace["z_challenge"]
-    for wit, polys_key, chal, point in (
-            ("aw_witness", "aw", trace["aw_challenge"], zc),
-            ("saw_witness", "saw", trace["saw_challenge"], zc * Domain.for_size(f, pk.n).group_gen % p)):
-        polys = trace[polys_key + "_polys"] if polys_key + "_polys" in trace else None
-        if polys is None:
-            continue
-        comb_tau = comb_z = 0
-        cur = 1
-        for q in polys:
-            comb_tau = (comb_tau + cur * poly_eval(f, q, tau)) % p
-            comb_z = (comb_z + cur * poly_eval(f, q, point)) % p
-            cur = cur * chal % p
-        if poly_eval(f, trace[wit], tau) * (tau - point) % p != (comb_tau - comb_z) % p:
-            return False
-    return True
