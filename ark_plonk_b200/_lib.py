@@ -57,6 +57,8 @@ class Lib:
         c.apb_g1_add.argtypes = [ci, vp, vp, vp]
         c.apb_msm_totals.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), ci]
         c.apb_msm_totals.restype = None
+        c.apb_ntt_totals.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), ci]
+        c.apb_ntt_totals.restype = None
         c.apb_domain_new.argtypes = [ci, C.c_uint32, C.POINTER(vp)]
         c.apb_domain_size.argtypes = [vp, C.POINTER(sz)]
         c.apb_domain_free.argtypes = [vp]
@@ -128,6 +130,11 @@ class Lib:
         ms, pts = C.c_double(), C.c_ulonglong()
         self.c.apb_msm_totals(C.byref(ms), C.byref(pts), 1 if reset else 0)
         return ms.value, pts.value
+
+    def ntt_totals(self, reset: bool = False):
+        ms, cnt = C.c_double(), C.c_ulonglong()
+        self.c.apb_ntt_totals(C.byref(ms), C.byref(cnt), 1 if reset else 0)
+        return ms.value, cnt.value
 
     def g1_add(self, curve: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint64)

@@ -25,6 +25,9 @@
 namespace apb {
 
 extern int g_num_sms;
+extern int g_profile;
+double g_ntt_ms_total = 0.0;              // device time of transforms while profiling (apb_set_profiling)
+unsigned long long g_ntt_count = 0;
 static const int COSET_LO_BITS = 10;
 
 struct NttPassArgs {
@@ -397,12 +400,29 @@ extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, siz
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
     if (batch == 0) return APB_OK;
     if (!d_out || (!d_in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (g_profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, g_stream); }
     int rc = d->curve == APB_CURVE_BLS12_381
                  ? run_ntt<Fr381>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch)
                  : run_ntt<Fr377>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch);
+    if (g_profile) {
+        cudaEventRecord(pe1, g_stream);
+        cudaEventSynchronize(pe1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe0, pe1);
+        g_ntt_ms_total += ms;
+        g_ntt_count += batch;
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    }
     if (rc != APB_OK) return rc;
     if (sync) APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
     return APB_OK;
+}
+
+extern "C" void apb_ntt_totals(double* ms, unsigned long long* transforms, int reset) {
+    if (ms) *ms = g_ntt_ms_total;
+    if (transforms) *transforms = g_ntt_count;
+    if (reset) { g_ntt_ms_total = 0.0; g_ntt_count = 0; }
 }
 
 extern "C" int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void* d_out, int sync) {

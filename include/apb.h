@@ -184,6 +184,8 @@ void apb_set_profiling(int on);
 void apb_msm_phase_ms(double out[4]);
 /* totals since the last reset while profiling: k_msm_accumulate milliseconds and scalars processed */
 void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset);
+/* totals since the last reset while profiling: device milliseconds and number of transforms */
+void apb_ntt_totals(double* ms, unsigned long long* transforms, int reset);
 /* milliseconds of device time of the last blocking apb_msm / apb_ntt call (CUDA events) */
 double apb_last_device_ms(void);
 
