@@ -9,7 +9,7 @@ the reference too (out of scope for the GPU).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -29,6 +29,7 @@ class CircuitArrays:
     values: list                # distinct field values (python ints)
     sigma: np.ndarray           # (4, n, 2) int64: sigma[col, row] = (col', row')
     table: list                 # lookup table rows (python ints)
+    public_inputs: dict = field(default_factory=dict)   # row -> value (non-zero entries only)
 
 
 def build(curve: int, degree: int, blinders) -> CircuitArrays:

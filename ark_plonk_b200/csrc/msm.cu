@@ -826,8 +826,10 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
 
-    // 7. host epilogue: Horner over weight bits, fold windows, normalise
+    // 7. host epilogue: Horner over weight bits, fold windows, then normalise all k results with ONE
+    //    field inversion (Montgomery's trick over the zz*zzz products)
     const host::Pt* V = reinterpret_cast<const host::Pt*>(ck->h_out);
+    std::vector<host::Pt> totals(B.k);
     for (uint32_t j = 0; j < B.k; j++) {
         host::Pt total_pt;
         grp.set_identity(total_pt);
@@ -843,9 +845,28 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
             for (uint32_t s = 0; s < g.c; s++) grp.dbl(total_pt, total_pt);
             grp.add(total_pt, total_pt, rows);
         }
+        totals[j] = total_pt;
+    }
+    std::vector<uint64_t> prod(6 * B.k), prefix(6 * B.k);
+    uint64_t run[6], inv[6];
+    f.set(run, f.one);
+    for (uint32_t j = 0; j < B.k; j++) {
+        f.set(&prefix[6 * j], run);
+        if (grp.is_identity(totals[j])) continue;
+        f.mul(&prod[6 * j], totals[j].zz, totals[j].zzz);
+        f.mul(run, run, &prod[6 * j]);
+    }
+    f.inv(inv, run);
+    for (int j = (int)B.k - 1; j >= 0; j--) {
         uint64_t* o = out_xyz + 18 * j;
-        uint64_t ax[6], ay[6];
-        if (!grp.to_affine(ax, ay, total_pt)) { write_identity(j); continue; }
+        if (grp.is_identity(totals[j])) { write_identity(j); continue; }
+        uint64_t pinv[6], zi2[6], zi3[6], ax[6], ay[6];
+        f.mul(pinv, inv, &prefix[6 * j]);            // 1 / (zz * zzz)
+        f.mul(inv, inv, &prod[6 * j]);
+        f.mul(zi2, pinv, totals[j].zzz);             // 1 / zz
+        f.mul(zi3, pinv, totals[j].zz);              // 1 / zzz
+        f.mul(ax, totals[j].x, zi2);
+        f.mul(ay, totals[j].y, zi3);
         memcpy(o, ax, 48);
         memcpy(o + 6, ay, 48);
         memcpy(o + 12, f.one, 48);

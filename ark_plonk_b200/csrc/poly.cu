@@ -313,9 +313,92 @@ struct QuotientArgs {
     const void *wl, *wr, *wo, *w4, *z, *z2, *f, *table, *h1, *h2, *pi;
     const void *q_m, *q_l, *q_r, *q_o, *q_4, *q_c, *q_arith, *q_lookup;
     const void *s1, *s2, *s3, *s4, *linear, *l1;
+    const void *q_range, *q_logic, *q_fixed, *q_var;          // custom gate selectors (NULL = identically zero)
     Fr4 alpha, beta, gamma, delta, epsilon, zeta, lookup_sep, k1, k2, k3;
+    Fr4 range_sep, logic_sep, fixed_sep, var_sep, coeff_a, coeff_d;   // embedded curve: a x^2 + y^2 = 1 + d x^2 y^2
     Fr4 vh_inv[4];
 };
+
+// f (f-1) (f-2) (f-3)   (widget/range.rs:64-73, widget/logic.rs:100-108)
+template <class FR>
+APB_D Fp<FR> gate_delta(const Fp<FR>& f) {
+    typedef Fp<FR> F;
+    const F one = F::one(), two = one + one, three = two + one;
+    return f * (f - one) * (f - two) * (f - three);
+}
+template <class FR>
+APB_D Fp<FR> small_const(uint32_t v) {          // v as a field element (Montgomery), by repeated addition
+    typedef Fp<FR> F;
+    F acc = F::zero(), cur = F::one();
+    for (; v; v >>= 1) {
+        if (v & 1) acc = acc + cur;
+        cur = cur + cur;
+    }
+    return acc;
+}
+// Range::constraints (widget/range.rs:46-62)
+template <class FR>
+APB_D Fp<FR> gate_range(const Fp<FR>& sep, const Fp<FR>& a, const Fp<FR>& b, const Fp<FR>& c, const Fp<FR>& d, const Fp<FR>& d_next) {
+    typedef Fp<FR> F;
+    const F kappa = sep.sqr(), kappa_sq = kappa.sqr(), kappa_cu = kappa_sq * kappa;
+    auto four = [](const F& x) { F t = x + x; return t + t; };
+    F b1 = gate_delta<FR>(c - four(d));
+    F b2 = gate_delta<FR>(b - four(c)) * kappa;
+    F b3 = gate_delta<FR>(a - four(b)) * kappa_sq;
+    F b4 = gate_delta<FR>(d_next - four(a)) * kappa_cu;
+    return (b1 + b2 + b3 + b4) * sep;
+}
+// Logic::constraints (widget/logic.rs:66-98) with delta_xor_and (:119-141)
+template <class FR>
+APB_D Fp<FR> gate_logic(const Fp<FR>& sep, const Fp<FR>& av, const Fp<FR>& bv, const Fp<FR>& cv, const Fp<FR>& dv, const Fp<FR>& a_next,
+                        const Fp<FR>& b_next, const Fp<FR>& d_next, const Fp<FR>& q_c) {
+    typedef Fp<FR> F;
+    const F kappa = sep.sqr(), kappa_sq = kappa.sqr(), kappa_cu = kappa_sq * kappa, kappa_qu = kappa_cu * kappa;
+    auto four = [](const F& x) { F t = x + x; return t + t; };
+    const F a = a_next - four(av), b = b_next - four(bv), d = d_next - four(dv), w = cv;
+    F c0 = gate_delta<FR>(a);
+    F c1 = gate_delta<FR>(b) * kappa;
+    F c2 = gate_delta<FR>(d) * kappa_sq;
+    F c3 = (w - a * b) * kappa_cu;
+    const F k3 = small_const<FR>(3), k9 = small_const<FR>(9), k18 = small_const<FR>(18), k81 = small_const<FR>(81),
+            k83 = small_const<FR>(83);
+    const F ab = a + b;
+    F Fv = w * (w * (four(w) - k18 * ab + k81) + k18 * (a.sqr() + b.sqr()) - k81 * ab + k83);
+    F E = k3 * (ab + d) - (Fv + Fv);
+    F Bv = q_c * (k9 * d - k3 * ab);
+    F c4 = (Bv + E) * kappa_qu;
+    return (c0 + c1 + c2 + c3 + c4) * sep;
+}
+// FixedBaseScalarMul::constraints (widget/ecc/fixed_base_scalar_mul.rs:88-156)
+template <class FR>
+APB_D Fp<FR> gate_fixed_base(const Fp<FR>& sep, const Fp<FR>& acc_x, const Fp<FR>& acc_y, const Fp<FR>& xy_alpha, const Fp<FR>& acc_bit,
+                             const Fp<FR>& acc_x_next, const Fp<FR>& acc_y_next, const Fp<FR>& acc_bit_next, const Fp<FR>& q_l,
+                             const Fp<FR>& q_r, const Fp<FR>& q_c, const Fp<FR>& coeff_a, const Fp<FR>& coeff_d) {
+    typedef Fp<FR> F;
+    const F kappa = sep.sqr(), kappa_sq = kappa.sqr(), kappa_cu = kappa_sq * kappa, one = F::one();
+    const F bit = acc_bit_next - acc_bit - acc_bit;
+    F bit_consistency = bit * (bit - one) * (bit + one);
+    const F y_alpha = bit.sqr() * (q_r - one) + one;
+    const F x_alpha = q_l * bit;
+    F xy_consistency = (bit * q_c - xy_alpha) * kappa;
+    const F t = xy_alpha * acc_x * acc_y * coeff_d;
+    F x_acc = ((acc_x_next + acc_x_next * t) - (x_alpha * acc_y + y_alpha * acc_x)) * kappa_sq;
+    F y_acc = ((acc_y_next - acc_y_next * t) - (y_alpha * acc_y - coeff_a * x_alpha * acc_x)) * kappa_cu;
+    return (bit_consistency + x_acc + y_acc + xy_consistency) * sep;
+}
+// CurveAddition::constraints (widget/ecc/curve_addition.rs:62-96)
+template <class FR>
+APB_D Fp<FR> gate_curve_add(const Fp<FR>& sep, const Fp<FR>& x1, const Fp<FR>& y1, const Fp<FR>& x2, const Fp<FR>& y2, const Fp<FR>& x3,
+                            const Fp<FR>& y3, const Fp<FR>& x1_y2, const Fp<FR>& coeff_a, const Fp<FR>& coeff_d) {
+    typedef Fp<FR> F;
+    const F kappa = sep.sqr();
+    F xy_consistency = x1 * y2 - x1_y2;
+    const F y1_x2 = y1 * x2, y1_y2 = y1 * y2, x1_x2 = x1 * x2;
+    const F t = coeff_d * x1_y2 * y1_x2;
+    F x3_consistency = ((x1_y2 + y1_x2) - (x3 + x3 * t)) * kappa;
+    F y3_consistency = ((y1_y2 - coeff_a * x1_x2) - (y3 - y3 * t)) * kappa.sqr();
+    return (xy_consistency + x3_consistency + y3_consistency) * sep;
+}
 template <class FR>
 __global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, void* out, uint64_t n4) {
     typedef Fp<FR> F;
@@ -329,6 +412,22 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, void* out, uin
              c * load_fp<FR>(A.q_o, i) + d * load_fp<FR>(A.q_4, i) + load_fp<FR>(A.q_c, i);
     gate = gate * load_fp<FR>(A.q_arith, i);
     if (A.pi) gate = gate + load_fp<FR>(A.pi, i);
+    // custom gates (quotient_poly.rs:231-264): selector * constraints(separation challenge, wires, next-row wires)
+    if (A.q_range || A.q_logic || A.q_fixed || A.q_var) {
+        const F an = load_fp<FR>(A.wl, j), bn = load_fp<FR>(A.wr, j), dn = load_fp<FR>(A.w4, j);
+        if (A.q_range) gate = gate + load_fp<FR>(A.q_range, i) * gate_range<FR>(arg_fp<FR>(A.range_sep.v), a, b, c, d, dn);
+        if (A.q_logic)
+            gate = gate + load_fp<FR>(A.q_logic, i) *
+                              gate_logic<FR>(arg_fp<FR>(A.logic_sep.v), a, b, c, d, an, bn, dn, load_fp<FR>(A.q_c, i));
+        if (A.q_fixed)
+            gate = gate + load_fp<FR>(A.q_fixed, i) *
+                              gate_fixed_base<FR>(arg_fp<FR>(A.fixed_sep.v), a, b, c, d, an, bn, dn, load_fp<FR>(A.q_l, i),
+                                                  load_fp<FR>(A.q_r, i), load_fp<FR>(A.q_c, i), arg_fp<FR>(A.coeff_a.v),
+                                                  arg_fp<FR>(A.coeff_d.v));
+        if (A.q_var)
+            gate = gate + load_fp<FR>(A.q_var, i) * gate_curve_add<FR>(arg_fp<FR>(A.var_sep.v), a, b, c, d, an, bn, dn,
+                                                                         arg_fp<FR>(A.coeff_a.v), arg_fp<FR>(A.coeff_d.v));
+    }
     // permutation
     const F zi = load_fp<FR>(A.z, i), zn = load_fp<FR>(A.z, j);
     const F l1 = load_fp<FR>(A.l1, i);
@@ -649,26 +748,41 @@ extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d
     return APB_OK;
 }
 
-// args mirror struct QuotientArgs; passed as a flat table of 25 pointers + 10 scalars + 4 inverse values
-extern "C" int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* scalars10, const uint64_t* vh_inv4, void* d_out,
-                                  size_t n4) {
+// args mirror struct QuotientArgs: 29 pointers (wl wr wo w4 z z2 f table h1 h2 pi | q_m q_l q_r q_o q_4 q_c q_arith
+// q_lookup | s1 s2 s3 s4 linear l1 | q_range q_logic q_fixed q_var), 16 scalars (alpha beta gamma delta epsilon zeta
+// lookup_sep K1 K2 K3 | range_sep logic_sep fixed_sep var_sep coeff_a coeff_d), 4 inverse vanishing values
+extern "C" int apb_plonk_quotient_full(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
+                                       void* d_out, size_t n4) {
     APB_API_LOCK();
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: bad curve");
-    if (!ptrs25 || !scalars10 || !vh_inv4 || !d_out) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null argument");
+    if (!ptrs29 || !scalars16 || !vh_inv4 || !d_out) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null argument");
     APB_REQUIRE_INIT();
     QuotientArgs A;
     const void** dst = &A.wl;
-    for (int i = 0; i < 25; i++) {
-        dst[i] = ptrs25[i];
-        if (!ptrs25[i] && i != 10) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null vector %d", i);
+    for (int i = 0; i < 29; i++) {
+        dst[i] = ptrs29[i];
+        if (!ptrs29[i] && i != 10 && i < 25) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null vector %d", i);
     }
     Fr4* sc = &A.alpha;
-    for (int i = 0; i < 10; i++) sc[i] = mk4(scalars10 + 4 * i);
+    for (int i = 0; i < 16; i++) sc[i] = mk4(scalars16 + 4 * i);
     for (int i = 0; i < 4; i++) A.vh_inv[i] = mk4(vh_inv4 + 4 * i);
     DISPATCH_FR(curve, APB_KLAUNCH(k_quotient<Fr381>, nblk(n4, 128), 128, 0, A, d_out, (uint64_t)n4),
                 APB_KLAUNCH(k_quotient<Fr377>, nblk(n4, 128), 128, 0, A, d_out, (uint64_t)n4));
     APB_CHECK_LAUNCH();
     return APB_OK;
+}
+
+// arithmetic + permutation + lookup terms only (all custom gate selectors identically zero)
+extern "C" int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* scalars10, const uint64_t* vh_inv4, void* d_out,
+                                  size_t n4) {
+    if (!ptrs25 || !scalars10) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null argument");
+    const void* p[29];
+    uint64_t sc[16 * 4];
+    for (int i = 0; i < 25; i++) p[i] = ptrs25[i];
+    for (int i = 25; i < 29; i++) p[i] = nullptr;
+    memset(sc, 0, sizeof(sc));
+    memcpy(sc, scalars10, 10 * 32);
+    return apb_plonk_quotient_full(curve, p, sc, vh_inv4, d_out, n4);
 }
 
 // k evaluations p_j(x_j); results (Montgomery) in host memory; blocking

@@ -9,9 +9,10 @@ the pointwise loops between them run as CUDA kernels (`apb_plonk_*`, `apb_fr_lin
 `apb_poly_*`), so polynomials never leave HBM.  The host handles the Fiat-Shamir transcript
 (`apb_transcript_*`), ~50 scalar field operations per proof (Python ints) and proof assembly.
 
-Scope: gate terms are implemented for the selectors the benchmark circuit uses (arithmetic,
-permutation, lookup).  Range / logic / ECC selectors must be identically zero (they are in
-`BenchCircuit`, composer.rs:506-509,531-534); `preprocess` rejects anything else.
+Scope: all of the reference's gate terms -- arithmetic, permutation, lookup, and the range /
+logic / fixed-base / curve-addition custom gates (widget/*.rs) -- and public inputs.  A custom
+gate selector that is identically zero (all four are in `BenchCircuit`, composer.rs:506-509,
+531-534) costs nothing: no resident vectors, no term in the kernel.
 There is no CPU fallback: all vector work goes through the CUDA library.
 """
 from __future__ import annotations
@@ -22,12 +23,14 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import encoding as enc
+from . import gates
 from ._lib import NTT_COSET_FFT, NTT_COSET_IFFT, NTT_FFT, NTT_IFFT, ApbError, Lib, get_lib
 from .bench_circuit import SELECTORS, CircuitArrays
 from .domain import Radix2EvaluationDomain
 from .kzg import CommitterKey
 
 K1, K2, K3 = 7, 13, 17
+CUSTOM_SELECTORS = ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add")
 FR_GENERATOR = (7, 22)
 
 
@@ -140,6 +143,8 @@ class ProverKey:
     vh_inv: np.ndarray = None                       # (4, 4) Montgomery
     commitments: dict = field(default_factory=dict) # verifier-key commitments, compressed bytes
     q_lookup_evals: int = 0                         # offset: q_lookup on the n-domain (prover.rs:252-254)
+    custom: tuple = ()                              # the custom gate selectors that are not identically zero
+    public_inputs: dict = field(default_factory=dict)
 
 
 class Prover:
@@ -202,18 +207,20 @@ class Prover:
     def preprocess(self, circ: CircuitArrays, commit_verifier_key: bool = True) -> ProverKey:
         curve, n, p = self.curve, circ.n, self.p
         lib = self.lib
-        for s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
-            if np.any(np.array(circ.values, dtype=object)[circ.selectors[s]] != 0):
-                raise ApbError(1, "gate selector %s is not identically zero: unsupported by this prover" % s)
+        # a custom gate selector that is identically zero contributes nothing to the quotient or the
+        # linearisation polynomial and commits to the identity: it gets no resident vectors
+        vals_obj = np.array(circ.values, dtype=object)
+        custom = tuple(s for s in CUSTOM_SELECTORS if np.any(vals_obj[circ.selectors[s]] != 0))
         dom = Radix2EvaluationDomain(curve, n, lib=lib)
         dom4 = Radix2EvaluationDomain(curve, 4 * n, lib=lib)
-        names = [s for s in SELECTORS if s not in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add")]
+        names = [s for s in SELECTORS if s not in CUSTOM_SELECTORS or s in custom]
         sig_names = ["left_sigma", "right_sigma", "out_sigma", "fourth_sigma"]
         # residents: (8 selectors + 4 sigmas) polys + 4 tables + q_lookup evals + scratch ; 14 vectors of 4n
         # + the per-proof working set of `prove` (24 n-vectors, 11 4n-vectors, openings)
-        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 30) * n + (len(names) + 4 + 2 + 11) * 4 * n,
+        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 32) * n + (len(names) + 4 + 2 + 12) * 4 * n,
                       torch_device=self.arena_device)
-        pk = ProverKey(curve=curve, n=n, arena=arena, dom=dom, dom4=dom4)
+        pk = ProverKey(curve=curve, n=n, arena=arena, dom=dom, dom4=dom4, custom=custom,
+                       public_inputs={int(k): int(v) % p for k, v in circ.public_inputs.items() if int(v) % p})
         vals_mont = _mont_list(curve, circ.values)
         tmp = arena.alloc(n)
         # selector polynomials: ifft of the evaluation columns (preprocess.rs:304-340)
@@ -318,7 +325,11 @@ class Prover:
 
     def _prove(self, pk, wires_mont, label, faithful, T, A, dom, dom4, n, N4, p, curve, lib, wires_resident=None):
         tr = Transcript(lib, curve, label)
-        tr.append_bytes(b"pi", (0).to_bytes(8, "little"))
+        # PublicInputs (proof_system/pi.rs) = BTreeMap<usize, F>: u64 length, (u64 row, element) in row order
+        pi_ser = len(pk.public_inputs).to_bytes(8, "little")
+        for pos in sorted(pk.public_inputs):
+            pi_ser += pos.to_bytes(8, "little") + pk.public_inputs[pos].to_bytes(32, "little")
+        tr.append_bytes(b"pi", pi_ser)
         omega = self._root_of_unity(n)
 
         # -- round 1: wire polynomials (prover.rs:188-220)
@@ -393,20 +404,33 @@ class Prover:
         fixed_sep = tr.challenge(b"fixed base separation challenge"); tr.append_fr(b"fixed base separation challenge", fixed_sep)
         var_sep = tr.challenge(b"variable base separation challenge"); tr.append_fr(b"variable base separation challenge", var_sep)
         lookup_sep = tr.challenge(b"lookup separation challenge"); tr.append_fr(b"lookup separation challenge", lookup_sep)
+        pi_poly = None
+        if pk.public_inputs:                                                 # prover.rs:400 (pi_poly = ifft of the PI column)
+            pi_col = np.zeros((n, 4), dtype=np.uint64)
+            rows = sorted(pk.public_inputs)
+            pi_col[rows] = _mont_list(curve, [pk.public_inputs[r] for r in rows])
+            pi_poly = A.alloc(n)
+            A.upload(pi_poly, pi_col)
+            self._ntt(dom, NTT_IFFT, A, pi_poly, n, pi_poly)
         mark4 = A.mark()
-        ev = A.alloc(10 * N4)
         srcs = [z_poly, wp[0], wp[1], wp[2], wp[3], z2_poly, f_poly, table_poly, h1_poly, h2_poly]
+        ev_names = ["z", "wl", "wr", "wo", "w4", "z2", "f", "table", "h1", "h2"]
+        if pi_poly is not None:
+            srcs.append(pi_poly)
+            ev_names.append("pi")
+        ev = A.alloc(len(srcs) * N4)
         for k, s in enumerate(srcs):                                         # 10 coset FFTs on 4n (quotient_poly.rs:74-120)
             self._ntt(dom4, NTT_COSET_FFT, A, s, n, ev + k * N4)
-        E = {nm: ev + k * N4 for k, nm in enumerate(("z", "wl", "wr", "wo", "w4", "z2", "f", "table", "h1", "h2"))}
+        E = {nm: ev + k * N4 for k, nm in enumerate(ev_names)}
         q_ev = A.alloc(N4)
-        order = [E["wl"], E["wr"], E["wo"], E["w4"], E["z"], E["z2"], E["f"], E["table"], E["h1"], E["h2"], None,
+        order = [E["wl"], E["wr"], E["wo"], E["w4"], E["z"], E["z2"], E["f"], E["table"], E["h1"], E["h2"], E.get("pi"),
                  pk.ev4["q_m"], pk.ev4["q_l"], pk.ev4["q_r"], pk.ev4["q_o"], pk.ev4["q_4"], pk.ev4["q_c"], pk.ev4["q_arith"],
                  pk.ev4["q_lookup"], pk.ev4["left_sigma"], pk.ev4["right_sigma"], pk.ev4["out_sigma"], pk.ev4["fourth_sigma"],
-                 pk.ev4["linear"], pk.ev4["l1"]]
-        ptrs = (C.c_void_p * 25)(*[A.ptr(o) if o is not None else None for o in order])
-        scal = _mont_list(curve, [alpha, beta, gamma, delta, epsilon, zeta, lookup_sep, K1, K2, K3])
-        lib.check(lib.c.apb_plonk_quotient(curve, ptrs, scal.ctypes.data, pk.vh_inv.ctypes.data, A.ptr(q_ev), N4))
+                 pk.ev4["linear"], pk.ev4["l1"]] + [pk.ev4.get(s) for s in CUSTOM_SELECTORS]
+        ptrs = (C.c_void_p * 29)(*[A.ptr(o) if o is not None else None for o in order])
+        scal = _mont_list(curve, [alpha, beta, gamma, delta, epsilon, zeta, lookup_sep, K1, K2, K3,
+                                  range_sep, logic_sep, fixed_sep, var_sep, gates.EMBEDDED_A[curve], gates.EMBEDDED_D[curve]])
+        lib.check(lib.c.apb_plonk_quotient_full(curve, ptrs, scal.ctypes.data, pk.vh_inv.ctypes.data, A.ptr(q_ev), N4))
         # the evaluation vectors are dead: t_poly reuses their space (the stream is in order, so
         # the coset_ifft reads q_ev before anything enqueued later can overwrite it)
         A.release(mark4)
@@ -449,6 +473,18 @@ class Prover:
             (t_off[0], -vanishing), (t_off[1], -vanishing * z_n), (t_off[2], -vanishing * z_n % p * z_n),
             (t_off[3], -vanishing * pow(z_n, 3, p)),
         ]
+        # custom gates: selector polynomial * constraints(evaluations) (linearisation_poly.rs:382-410)
+        w_e, nxt_e = (a_e, b_e, c_e, d_e), (a_next, b_next, d_next)
+        for s in pk.custom:
+            if s == "q_range":
+                sc = gates.range_scalar(range_sep, w_e, nxt_e, p)
+            elif s == "q_logic":
+                sc = gates.logic_scalar(logic_sep, w_e, nxt_e, q_c_e, p)
+            elif s == "q_fixed_group_add":
+                sc = gates.fixed_base_scalar(fixed_sep, w_e, nxt_e, q_l_e, q_r_e, q_c_e, curve, p)
+            else:
+                sc = gates.curve_add_scalar(var_sep, w_e, nxt_e, curve, p)
+            terms.append((P[s], sc))
         lin_poly = A.alloc(n)
         self._lincomb(A, [o for o, _ in terms], [n] * len(terms), [s % p for _, s in terms], lin_poly, n)
         for lab, v in ((b"a_eval", a_e), (b"b_eval", b_e), (b"c_eval", c_e), (b"d_eval", d_e), (b"left_sig_eval", left_e),

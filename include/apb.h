@@ -147,6 +147,12 @@ int apb_plonk_lookup_z2(apb_domain_t dom, const void* d_f, const void* d_t, cons
  * lookup_sep K1 K2 K3 ; vh_inv4 = inverses of the 4-periodic vanishing-polynomial values */
 int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* scalars10, const uint64_t* vh_inv4,
                        void* d_out, size_t n4);
+/* same with the custom gate terms of quotient_poly.rs:231-264 (widget/range.rs, widget/logic.rs,
+ * widget/ecc/fixed_base_scalar_mul.rs, widget/ecc/curve_addition.rs): ptrs29 = the 25 above + q_range q_logic
+ * q_fixed_group_add q_variable_group_add (NULL = identically zero); scalars16 = the 10 above + the range / logic /
+ * fixed-base / variable-base separation challenges + the embedded curve's COEFF_A, COEFF_D */
+int apb_plonk_quotient_full(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
+                            void* d_out, size_t n4);
 /* k evaluations polys[j](points[j]) -> out_vals (host, Montgomery); DensePolynomial::evaluate */
 int apb_poly_eval(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* points,
                   uint64_t* out_vals);

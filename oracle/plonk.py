@@ -27,6 +27,7 @@ from dataclasses import dataclass, field
 
 from .curves import CURVES, Curve
 from .merlin import Transcript
+from . import gates
 from .ntt import Domain, poly_eval
 from .serialize import ser_field, ser_g1, ser_kzg_proof, ser_string, ser_u64
 
@@ -35,7 +36,7 @@ LEFT, RIGHT, OUT, FOURTH = 0, 1, 2, 3
 
 
 # --------------------------------------------------------------------------------------------
-# constraint system (only what the benchmark circuit touches)
+# constraint system: the benchmark circuit's rows plus the arithmetic / range / logic / ECC gadgets
 # --------------------------------------------------------------------------------------------
 class Composer:
     SELECTORS = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_4", "q_arith", "q_range", "q_logic",
@@ -53,6 +54,7 @@ class Composer:
         self.variables = []                        # id -> value
         self.variable_map = []                     # id -> [(wire, row)]
         self.lookup_table = []                     # rows [a, b, c, d]
+        self.public_inputs = {}                    # row -> value (proof_system/pi.rs: zero values are not stored)
         self.zero_var = self.add_input(0)
         # constrain_to_constant(zero, 0): poly_gate(a, a, a, 0, 1, 0, 0, -0)
         self._push_row((self.zero_var,) * 3 + (self.zero_var,), q_l=1, q_arith=1)
@@ -67,9 +69,183 @@ class Composer:
         for col, var in enumerate(wires):
             self.w[col].append(var)
             self.variable_map[var].append((col, self.n))
+        self._push_selectors(**sel)
+        self.n += 1
+
+    def _push_selectors(self, **sel):
         for s in self.SELECTORS:
             getattr(self, s).append(sel.get(s, 0) % self.p)
+
+    def _map(self, var, col, row):
+        self.variable_map[var].append((col, row))
+
+    def value(self, var: int) -> int:
+        return self.variables[var]
+
+    # ---- arithmetic gadgets (constraint_system/composer.rs:269-351, arithmetic.rs:100-163) ----------
+    def poly_gate(self, a, b, c, q_m, q_l, q_r, q_o, q_c, pi=None):
+        if pi is not None:
+            self._add_pi(self.n, pi)
+        self._push_row((a, b, c, self.zero_var), q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, q_arith=1)
+        return a, b, c
+
+    def _add_pi(self, pos, value):
+        assert pos not in self.public_inputs, "Insertion in public inputs conflicts with previous value"
+        if value % self.p:
+            self.public_inputs[pos] = value % self.p
+
+    def constrain_to_constant(self, a, constant, pi=None):
+        self.poly_gate(a, a, a, 0, 1, 0, 0, -constant, pi)
+
+    def assert_equal(self, a, b):
+        self.poly_gate(a, b, self.zero_var, 0, 1, -1, 0, 0)
+
+    def arithmetic_gate(self, w_l, w_r, w_o=None, q_m=0, q_l=0, q_r=0, q_o=-1, q_c=0, q_4=0, w_4=None, pi=None):
+        """ArithmeticGate builder: witness(w_l, w_r, w_o), fan_in_3(q_4, w_4), mul, add, out, constant, pi"""
+        p = self.p
+        w_4 = self.zero_var if w_4 is None else w_4
+        if pi is not None:
+            self._add_pi(self.n, pi)
+        if w_o is None:
+            v = (q_m * self.variables[w_l] * self.variables[w_r] + q_l * self.variables[w_l] + q_r * self.variables[w_r]
+                 + q_c + q_4 * self.variables[w_4] + (pi or 0)) * (-q_o)
+            w_o = self.add_input(v)
+        self._push_row((w_l, w_r, w_o, w_4), q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, q_4=q_4, q_arith=1)
+        return w_o
+
+    # ---- range (constraint_system/range.rs:27-190) ---------------------------------------------------
+    def range_gate(self, witness: int, num_bits: int):
+        assert num_bits % 2 == 0
+        value = self.variables[witness]
+        num_gates = (num_bits >> 3) + (1 if num_bits % 8 else 0)
+        num_quads = num_gates * 4
+        pad = 1 + (((num_quads << 1) - num_bits) >> 1)
+        used_gates = num_gates + 1
+        first = self.n
+        cols = (FOURTH, OUT, RIGHT, LEFT)                  # accumulator i sits in column i % 4 of row first + i / 4
+
+        def add_wire(i, var):
+            col = cols[i % 4]
+            self.w[col].append(var)
+            self._map(var, col, first + i // 4)
+
+        for i in range(pad):
+            add_wire(i, self.zero_var)
+        accumulators = []
+        acc = 0
+        for i in range(pad, num_quads + 1):
+            bit_index = (num_quads - i) << 1
+            quad = ((value >> bit_index) & 1) + 2 * ((value >> (bit_index + 1)) & 1)
+            acc = (4 * acc + quad) % self.p
+            var = self.add_input(acc)
+            accumulators.append(var)
+            add_wire(i, var)
+        for g in range(used_gates):
+            self._push_selectors(q_range=1 if g < used_gates - 1 else 0)
+        self.n += used_gates
+        for col in (LEFT, RIGHT, OUT):                     # last row: zero wires, NOT entered in the permutation
+            self.w[col].append(self.zero_var)
+        self.assert_equal(accumulators[-1], witness)
+
+    # ---- logic (constraint_system/logic.rs:30-325) ---------------------------------------------------
+    def logic_gate(self, a: int, b: int, num_bits: int, is_xor: bool) -> int:
+        assert num_bits & 1 == 0
+        num_quads = num_bits >> 1
+        av, bv = self.variables[a], self.variables[b]
+        a_bits = [(av >> (num_bits - 1 - k)) & 1 for k in range(num_bits)]       # big endian, low num_bits bits
+        b_bits = [(bv >> (num_bits - 1 - k)) & 1 for k in range(num_bits)]
+        Z = self.zero_var
+        for col in (LEFT, RIGHT, FOURTH):
+            self._map(Z, col, self.n)
+            self.w[col].append(Z)
         self.n += 1
+        la = ra = oa = 0
+        for i in range(num_quads):
+            lq = (a_bits[2 * i] << 1) + a_bits[2 * i + 1]
+            rq = (b_bits[2 * i] << 1) + b_bits[2 * i + 1]
+            oq = (lq ^ rq) if is_xor else (lq & rq)
+            la, ra, oa = (4 * la + lq) % self.p, (4 * ra + rq) % self.p, (4 * oa + oq) % self.p
+            va, vb, vc, v4 = self.add_input(la), self.add_input(ra), self.add_input(lq * rq), self.add_input(oa)
+            self._map(va, LEFT, self.n)
+            self._map(vb, RIGHT, self.n)
+            self._map(v4, FOURTH, self.n)
+            self._map(vc, OUT, self.n - 1)
+            self.w[LEFT].append(va)
+            self.w[RIGHT].append(vb)
+            self.w[OUT].append(vc)
+            self.w[FOURTH].append(v4)
+            self.n += 1
+        self._map(Z, OUT, self.n - 1)
+        self.w[OUT].append(Z)
+        sgn = -1 if is_xor else 1
+        for _ in range(num_quads):
+            self._push_selectors(q_c=sgn, q_logic=sgn)
+        self._push_selectors()
+        return self.w[FOURTH][-1]
+
+    def xor_gate(self, a, b, num_bits):
+        return self.logic_gate(a, b, num_bits, True)
+
+    def and_gate(self, a, b, num_bits):
+        return self.logic_gate(a, b, num_bits, False)
+
+    # ---- embedded curve (constraint_system/ecc/curve_addition/*.rs, ecc/scalar_mul/fixed_base.rs) ---
+    def point_addition_gate(self, pa, pb):
+        """pa, pb: (x var, y var); returns the (x, y) variables of the sum (variable_base_gate.rs:23-97)"""
+        from . import gates
+        A, D = gates.embedded_params(self.curve)
+        p = self.p
+        x1, y1, x2, y2 = pa[0], pa[1], pb[0], pb[1]
+        x1s, y1s, x2s, y2s = (self.variables[v] for v in (x1, y1, x2, y2))
+        x3s, y3s = gates.te_add((x1s, y1s), (x2s, y2s), A, D, p)
+        x1_y2 = self.add_input(x1s * y2s)
+        x3, y3 = self.add_input(x3s), self.add_input(y3s)
+        self._push_row((x1, y1, x2, y2), q_variable_group_add=1)
+        self._push_row((x3, y3, self.zero_var, x1_y2))
+        return x3, y3
+
+    def fixed_base_scalar_mul(self, scalar: int, base_point):
+        """scalar: variable; base_point: affine (x, y) on the embedded curve (fixed_base.rs:52-173)"""
+        from . import gates
+        A, D = gates.embedded_params(self.curve)
+        p = self.p
+        num_bits = self.curve.fr.bits
+        mult = [base_point]
+        for _ in range(1, num_bits):
+            mult.append(gates.te_add(mult[-1], mult[-1], A, D, p))
+        mult.reverse()
+        wnaf = gates.find_wnaf2(self.variables[scalar])
+        assert len(wnaf) <= num_bits
+        ntz = num_bits - len(wnaf)
+        scalar_acc = [0] * (1 + ntz)
+        point_acc = [(0, 1)] * (1 + ntz)
+        xy_alphas = [0] * ntz
+        for i, entry in enumerate(reversed(wnaf)):
+            index = i + ntz
+            if entry == 0:
+                s_add, pt = 0, (0, 1)
+            elif entry == 1:
+                s_add, pt = 1, mult[index]
+            else:
+                s_add, pt = -1, gates.te_neg(mult[index], p)
+            scalar_acc.append((2 * scalar_acc[index] + s_add) % p)
+            point_acc.append(gates.te_add(point_acc[index], pt, A, D, p))
+            xy_alphas.append(pt[0] * pt[1] % p)
+        for i in range(num_bits):
+            acc_x, acc_y = self.add_input(point_acc[i][0]), self.add_input(point_acc[i][1])
+            acc_bit = self.add_input(scalar_acc[i])
+            if i == 0:
+                self.constrain_to_constant(acc_x, 0)
+                self.constrain_to_constant(acc_y, 1)
+                self.constrain_to_constant(acc_bit, 0)
+            xb, yb = mult[i]
+            xy_alpha = self.add_input(xy_alphas[i])
+            self._push_row((acc_x, acc_y, xy_alpha, acc_bit), q_l=xb, q_r=yb, q_c=xb * yb, q_fixed_group_add=1)
+        acc_x, acc_y = self.add_input(point_acc[num_bits][0]), self.add_input(point_acc[num_bits][1])
+        last_bit = self.add_input(scalar_acc[num_bits])
+        self.arithmetic_gate(acc_x, acc_y, self.zero_var, q_o=0, q_4=0, w_4=last_bit)
+        self.assert_equal(last_bit, scalar)
+        return acc_x, acc_y
 
     def _add_blinding_factors(self, b):
         """composer.rs:580-648: two rows of 4 random wires, one row repeating the last pair."""
@@ -249,8 +425,6 @@ def preprocess(cs: Composer, kzg: Kzg) -> ProverKey:
     g_n = pow(f.generator, n, p)
     w4 = dom4.group_gen
     pk.v_h_coset = [(g_n * pow(w4, n * i, p) - 1) % p for i in range(4 * n)]
-    for s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
-        assert not pk.polys[s], "oracle restates range/logic/ecc gate terms only for zero selectors"
     return pk
 
 
@@ -296,7 +470,11 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
     dom4 = Domain.for_size(f, 4 * n)
     tr = PlonkTranscript(curve, transcript_label)
     T = trace if trace is not None else {}
-    tr.append_bytes(b"pi", ser_u64(0))                         # empty PublicInputs (BTreeMap) = u64 length 0
+    # PublicInputs = BTreeMap<usize, F>: u64 length, then (u64 position, field element) in key order
+    pi_ser = ser_u64(len(cs.public_inputs))
+    for pos in sorted(cs.public_inputs):
+        pi_ser += ser_u64(pos) + ser_field(f, cs.public_inputs[pos])
+    tr.append_bytes(b"pi", pi_ser)
 
     # ---- round 1: wires ------------------------------------------------------------------
     wires = []
@@ -367,7 +545,10 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
         z2.append(z2[-1] * num % p * pow(den, -1, p) % p)
     z2_poly = strip(dom.ifft(z2))
     z2_comm = kzg.commit(z2_poly)               # NOT appended to the transcript (prover.rs:387-389)
-    pi_poly = []                                # zero public inputs
+    pi_evals = [0] * n
+    for pos, v in cs.public_inputs.items():
+        pi_evals[pos] = v
+    pi_poly = strip(dom.ifft(pi_evals))
     T.update(beta=beta, gamma=gamma, delta=delta, epsilon=epsilon, z=z, z2=z2, z_poly=z_poly, z2_poly=z2_poly)
 
     # ---- round 4: quotient ---------------------------------------------------------------
@@ -388,6 +569,10 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
     E = pk.evals
     lsq = lookup_sep * lookup_sep % p
     lcu = lsq * lookup_sep % p
+    custom_names = ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add")
+    custom_on = [bool(pk.polys[s]) for s in custom_names]
+    seps = (range_sep, logic_sep, fixed_sep, var_sep)
+    EA, ED = gates.embedded_params(curve)
     quotient = []
     for i in range(N4):
         j = (i + 4) % N4
@@ -396,6 +581,10 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
         gate = (a * b % p * E["q_m"][i] + a * E["q_l"][i] + b * E["q_r"][i] + c * E["q_o"][i] + d * E["q_4"][i]
                 + E["q_c"][i]) % p * E["q_arith"][i] % p
         gate = (gate + ev["pi"][i]) % p
+        if any(custom_on):      # range / logic / fixed-base / curve-addition terms (quotient_poly.rs:231-264)
+            sel = [E[s][i] if on else None for s, on in zip(custom_names, custom_on)]
+            gate = (gate + sum(gates.custom_gate_sum(sel, seps, (a, b, c, d), (ev["wl"][j], ev["wr"][j], ev["w4"][j]),
+                                                     E["q_l"][i], E["q_r"][i], E["q_c"][i], EA, ED, p))) % p
         # permutation (proof_system/permutation.rs:62-155)
         x = pk.linear_evals[i]
         zi, zn = ev["z"][i], ev["z"][j]
@@ -420,7 +609,8 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
     t_comms = [kzg.commit(q) for q in t_parts]
     for lab, c in zip((b"t_1", b"t_2", b"t_3", b"t_4"), t_comms):
         tr.append_g1(lab, c)
-    T.update(alpha=alpha, lookup_sep=lookup_sep, quotient_evals=quotient, t_poly=t_poly, evals_4n=ev)
+    T.update(alpha=alpha, lookup_sep=lookup_sep, range_sep=range_sep, logic_sep=logic_sep, fixed_sep=fixed_sep,
+             var_sep=var_sep, quotient_evals=quotient, t_poly=t_poly, evals_4n=ev)
 
     # ---- round 5: linearisation + openings ----------------------------------------------
     zc = tr.challenge(b"z"); tr.append_fr(b"z", zc)
@@ -478,7 +668,11 @@ def prove(cs: Composer, pk: ProverKey, kzg: Kzg, transcript_label: bytes = b"ark
     qt = scale(add(qt, t_parts[2]), z_n)
     qt = scale(add(qt, t_parts[1]), z_n)
     qt = scale(add(qt, t_parts[0]), vanishing)
-    lin_poly = strip(add(arith, perm_lin, lk_a, lk_b, lk_c, scale(qt, p - 1)))
+    # custom gates: selector_poly * constraints(evaluations) (linearisation_poly.rs:382-410)
+    cg = gates.custom_gate_sum([1 if on else None for on in custom_on], seps, (a_eval, b_eval, c_eval, d_eval),
+                               (a_next, b_next, d_next), q_l_e, q_r_e, q_c_e, EA, ED, p)
+    custom_lin = add(*[scale(P[s], v) for s, v, on in zip(custom_names, cg, custom_on) if on])
+    lin_poly = strip(add(arith, custom_lin, perm_lin, lk_a, lk_b, lk_c, scale(qt, p - 1)))
 
     for lab, v in ((b"a_eval", a_eval), (b"b_eval", b_eval), (b"c_eval", c_eval), (b"d_eval", d_eval),
                    (b"left_sig_eval", left_e), (b"right_sig_eval", right_e), (b"out_sig_eval", out_e),

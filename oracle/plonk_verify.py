@@ -8,15 +8,17 @@ compressed table commitment (:316-325) and the two batched KZG checks (:345-425)
 
 The pairing equation of `PC::check`, e(C - v G, H) = e(W, tau H - z H), is evaluated in its
 discrete-log form in G1, C - v G == (tau - z) W, because the harness knows tau.
-Range / logic / ECC selector commitments are the identity for the benchmark circuit, so their
-linearisation terms vanish whatever their scalars are.
+Range / logic / fixed-base / curve-addition selector commitments enter through
+`extend_linearisation_commitment` (widget/mod.rs:152-170, proof.rs:530-559); public inputs through
+the barycentric pi_eval of compute_r0.
 """
 from __future__ import annotations
 
+from . import gates
 from .curves import Curve
 from .ntt import Domain
 from .plonk import K1, K2, K3, PlonkTranscript, lc
-from .serialize import deser_g1, ser_u64
+from .serialize import deser_g1, ser_field, ser_u64
 
 
 def parse_proof(curve: Curve, blob: bytes):
@@ -48,15 +50,20 @@ def parse_proof(curve: Curve, blob: bytes):
     return dict(zip(names, comms)), openings, evals, custom
 
 
-def verify(curve: Curve, vk: dict, n: int, blob: bytes, tau: int, label: bytes = b"ark") -> bool:
-    """vk: name -> affine point for q_m q_l q_r q_o q_4 q_c q_arith q_lookup left_sigma right_sigma
-    out_sigma fourth_sigma table_1..table_4 (missing selectors = identity)."""
+def verify(curve: Curve, vk: dict, n: int, blob: bytes, tau: int, label: bytes = b"ark", public_inputs=None) -> bool:
+    """vk: name -> affine point for q_m q_l q_r q_o q_4 q_c q_arith q_range q_logic q_fixed_group_add
+    q_variable_group_add q_lookup left_sigma right_sigma out_sigma fourth_sigma table_1..table_4
+    (missing selectors = identity).  public_inputs: row -> value."""
     p = curve.fr.p
     C, (aw_open, saw_open), ev, custom = parse_proof(curve, blob)
     (a_e, b_e, c_e, d_e, s1, s2, s3, zhat, q_lookup_e, z2_next, h1_e, h1_next, h2_e, f_e, table_e, table_next) = ev
     cust = dict(custom)
     tr = PlonkTranscript(curve, label)
-    tr.append_bytes(b"pi", ser_u64(0))
+    public_inputs = public_inputs or {}
+    pi_ser = ser_u64(len(public_inputs))
+    for pos in sorted(public_inputs):
+        pi_ser += ser_u64(pos) + ser_field(curve.fr, public_inputs[pos])
+    tr.append_bytes(b"pi", pi_ser)
     for lab, key in ((b"w_l", "a"), (b"w_r", "b"), (b"w_o", "c"), (b"w_4", "d")):
         tr.append_g1(lab, C[key])
     zeta = tr.challenge(b"zeta"); tr.append_fr(b"zeta", zeta)
@@ -67,11 +74,13 @@ def verify(curve: Curve, vk: dict, n: int, blob: bytes, tau: int, label: bytes =
     epsilon = tr.challenge(b"epsilon"); tr.append_fr(b"epsilon", epsilon)
     tr.append_g1(b"z", C["z"])
     alpha = tr.challenge(b"alpha"); tr.append_fr(b"alpha", alpha)
+    seps = []
     for ch, ap in ((b"range separation challenge", b"range seperation challenge"),
                    (b"logic separation challenge", b"logic seperation challenge"),
                    (b"fixed base separation challenge", b"fixed base separation challenge"),
                    (b"variable base separation challenge", b"variable base separation challenge")):
         v = tr.challenge(ch); tr.append_fr(ap, v)
+        seps.append(v)
     ls = tr.challenge(b"lookup separation challenge"); tr.append_fr(b"lookup separation challenge", ls)
     for lab, key in ((b"t_1", "t_1"), (b"t_2", "t_2"), (b"t_3", "t_3"), (b"t_4", "t_4")):
         tr.append_g1(lab, C[key])
@@ -83,8 +92,11 @@ def verify(curve: Curve, vk: dict, n: int, blob: bytes, tau: int, label: bytes =
     lsq, lcu = ls * ls % p, pow(ls, 3, p)
     opd = (1 + delta) % p
     eopd = epsilon * opd % p
-    # compute_r0 (public inputs are empty -> pi_eval = 0)
-    r0 = (0 - (a_e + beta * s1 + gamma) * (b_e + beta * s2 + gamma) % p * (c_e + beta * s3 + gamma) % p
+    # compute_r0 (proof.rs:426-486) with pi_eval by barycentric evaluation (proof.rs:635-677)
+    omega_inv = pow(Domain.for_size(curve.fr, n).group_gen, -1, p)
+    pi_eval = zh * pow(n, -1, p) % p * sum(v * pow((pow(omega_inv, pos, p) * zc - 1) % p, -1, p)
+                                           for pos, v in public_inputs.items()) % p
+    r0 = (pi_eval - (a_e + beta * s1 + gamma) * (b_e + beta * s2 + gamma) % p * (c_e + beta * s3 + gamma) % p
           * ((d_e + gamma) * zhat % p * alpha % p)
           - l1 * alpha_sq
           - lsq * z2_next % p * (eopd + delta * h2_e) % p * (eopd + h2_e + delta * h1_next)
@@ -101,6 +113,13 @@ def verify(curve: Curve, vk: dict, n: int, blob: bytes, tau: int, label: bytes =
     q_arith = cust["q_arith_eval"]
     terms = [(a_e * b_e % p * q_arith, vk.get("q_m")), (a_e * q_arith, vk.get("q_l")), (b_e * q_arith, vk.get("q_r")),
              (c_e * q_arith, vk.get("q_o")), (d_e * q_arith, vk.get("q_4")), (q_arith, vk.get("q_c"))]
+    # custom gates: selector commitment * constraints(evaluations) (proof.rs:530-559)
+    EA, ED = gates.embedded_params(curve)
+    cg = gates.custom_gate_sum([1, 1, 1, 1], seps, (a_e, b_e, c_e, d_e),
+                               (cust["a_next_eval"], cust["b_next_eval"], cust["d_next_eval"]),
+                               cust["q_l_eval"], cust["q_r_eval"], cust["q_c_eval"], EA, ED, p)
+    terms += list(zip(cg, (vk.get("q_range"), vk.get("q_logic"), vk.get("q_fixed_group_add"),
+                           vk.get("q_variable_group_add"))))
     terms.append(((lc([a_e, b_e, c_e, d_e], zeta, p) - f_e) * ls, vk.get("q_lookup")))
     terms.append((opd * (epsilon + f_e) % p * (eopd + table_e + delta * table_next) % p * lsq + l1 * lcu, C["z_2"]))
     terms.append(((-z2_next) * lsq % p * (eopd + h2_e + delta * h1_next), C["h_1"]))

@@ -115,6 +115,22 @@ def test_prover_2p18_verifies_under_restated_verifier(gpu_lib):
     ck.close()
 
 
+import gadget_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("kind", gadget_cases.KINDS)
+def test_prover_custom_gates_match_oracle(gpu_lib, curve, kind):
+    """circuits built from the reference's range / logic / curve-addition / fixed-base gadgets with public
+    inputs: CUDA proof == oracle proof byte for byte, accepted by the restated verifier"""
+    gadget_cases.prove_gadget_case(gpu_lib, curve, kind)
+
+
+def test_prover_custom_gates_reject_bad_witness(gpu_lib):
+    """a witness that breaks a gate constraint yields a proof the verifier rejects"""
+    gadget_cases.prove_gadget_case(gpu_lib, 0, "mixed", tamper=True)
+
+
 # ---- polynomial / prover kernels, unit parity -------------------------------------------------
 import poly_cases  # noqa: E402
 
