@@ -33,6 +33,8 @@ __global__ void k_field_op(int op, const void* a, const void* b, void* out, uint
         r = op == 0 ? x * y : (op == 1 ? x + y : x - y);
     } else if (op == 5) {
         r = x.sqr();
+    } else if (op == 6) {
+        r = x.is_zero() ? x : x.inverse_binary();
     } else {
         r = op == 3 ? x.to_mont() : x.from_mont();
     }
@@ -267,7 +269,7 @@ extern "C" int apb_dev_sync(void) {
 
 extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count) {
     APB_API_LOCK();
-    if (field < 0 || field > 3 || op < 0 || op > 5) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: bad field/op");
+    if (field < 0 || field > 3 || op < 0 || op > 6) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: bad field/op");
     if (!a || !out || (op <= 2 && !b)) return set_err(APB_ERR_INVALID_ARG, "apb_field_op: null argument");
     if (count == 0) return APB_OK;
     APB_REQUIRE_INIT();

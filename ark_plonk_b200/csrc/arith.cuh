@@ -274,6 +274,55 @@ struct Fp {
         o.v[0] = 1;
         return *this * o;
     }
+
+    // 1/a in Montgomery form by the binary extended Euclidean algorithm (shifts, adds, compares on
+    // the limbs: ~2 log2(p) halvings + log2(p) subtractions).  For ONE thread that must invert alone
+    // (the batched-inversion root in msm.cu) this is ~10x shorter than the a^(p-2) chain, whose
+    // ~570 dependent Montgomery products run at single-warp latency; it is data-dependent, so a
+    // warp whose lanes all invert should keep using the exponentiation.  a != 0.
+    APB_HD static void shr1(uint32_t* x) {
+        _Pragma("unroll") for (int i = 0; i < N - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+        x[N - 1] >>= 1;
+    }
+    APB_HD static void halve_mod(uint32_t* x) {          // x/2 mod p for x < p (p odd, p < 2^(32N-2))
+        if (x[0] & 1) {
+            x[0] = add_cc(x[0], P::mod(0));
+            _Pragma("unroll") for (int i = 1; i < N - 1; i++) x[i] = addc_cc(x[i], P::mod(i));
+            x[N - 1] = addc(x[N - 1], P::mod(N - 1));
+        }
+        shr1(x);
+    }
+    APB_HD static bool is_one_raw(const uint32_t* x) {
+        uint32_t acc = x[0] ^ 1u;
+        _Pragma("unroll") for (int i = 1; i < N; i++) acc |= x[i];
+        return acc == 0;
+    }
+    APB_HD static bool geq_raw(const uint32_t* a, const uint32_t* b) {
+        for (int i = N - 1; i >= 0; i--) {
+            if (a[i] > b[i]) return true;
+            if (a[i] < b[i]) return false;
+        }
+        return true;
+    }
+    APB_HD static void sub_raw(uint32_t* a, const uint32_t* b) {     // a -= b, a >= b
+        a[0] = sub_cc(a[0], b[0]);
+        _Pragma("unroll") for (int i = 1; i < N - 1; i++) a[i] = subc_cc(a[i], b[i]);
+        a[N - 1] = subc(a[N - 1], b[N - 1]);
+    }
+    APB_HD Fp inverse_binary() const {
+        Fp u = *this, w, x1 = zero(), x2 = zero();
+        _Pragma("unroll") for (int i = 0; i < N; i++) w.v[i] = P::mod(i);
+        x1.v[0] = 1;
+        while (!is_one_raw(u.v) && !is_one_raw(w.v)) {
+            while (!(u.v[0] & 1)) { shr1(u.v); halve_mod(x1.v); }
+            while (!(w.v[0] & 1)) { shr1(w.v); halve_mod(x2.v); }
+            if (geq_raw(u.v, w.v)) { sub_raw(u.v, w.v); x1 = x1 - x2; }
+            else { sub_raw(w.v, u.v); x2 = x2 - x1; }
+        }
+        // x = (aR)^-1 as a plain residue = a^-1 R^-1; two Montgomery products by R^2 give a^-1 R
+        const Fp x = is_one_raw(u.v) ? x1 : x2;
+        return (x * r2()) * r2();
+    }
 };
 
 }  // namespace apb

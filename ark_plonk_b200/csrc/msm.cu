@@ -162,7 +162,10 @@ APB_D void store_xyzz(void* arr, uint64_t idx, const XYZZ<FQ>& p) {
 
 // Each thread owns entries [t*E, (t+1)*E) of the bucket-sorted list.  The next point is
 // fetched (entry id, then the 96-byte affine record) while the current mixed add runs.
-template <class FQ, int MINB>
+// SRC 0: entry ids into the resident table (sign in bit 31; (0,0) = infinity).  SRC 1: the list is
+// itself an array of affine partial sums (output of the batched-affine pair levels below; infinity is
+// marked by an all-ones top limb of x), entry p is point p.
+template <class FQ, int MINB, int SRC>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
                                                               const void* bases, uint32_t E, void* bucket_sums, void* partials,
                                                               int32_t* part_bucket) {
@@ -185,9 +188,9 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* en
     // One flat loop over the chunk: every lane performs its mixed add in the same iteration
     // (bucket borders fall at different positions in different lanes; a nested run loop lets
     // the lanes drift apart and the warp then executes the add twice at half occupancy).
-    uint32_t e_cur = entries[pos];
+    uint32_t e_cur = SRC == 0 ? entries[pos] : 0u;
     F px, py;
-    load_affine<FQ>(bases, e_cur & 0x7fffffffu, px, py);
+    load_affine<FQ>(bases, SRC == 0 ? (uint64_t)(e_cur & 0x7fffffffu) : pos, px, py);
     uint64_t bstart = offsets[b], bend = offsets[b + 1], run_start = pos;
     XYZZ<FQ> acc = XYZZ<FQ>::identity();
     while (pos < end) {
@@ -195,10 +198,11 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* en
         F nx, ny;
         const bool more = pos + 1 < end;
         if (more) {
-            e_nxt = entries[pos + 1];
-            load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
+            if (SRC == 0) e_nxt = entries[pos + 1];
+            load_affine<FQ>(bases, SRC == 0 ? (uint64_t)(e_nxt & 0x7fffffffu) : pos + 1, nx, ny);
         }
-        if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
+        const bool inf = SRC == 0 ? (px.is_zero() && py.is_zero()) : (px.v[FQ::N - 1] == 0xffffffffu);
+        if (!inf) {                                          // skip the point at infinity
             if (e_cur >> 31) py = py.neg();
             acc.add_affine(px, py);
         }
@@ -403,6 +407,223 @@ __device__ __noinline__ Fp<FQ> fp_inverse(const Fp<FQ>& a) {
     return acc;
 }
 
+// ---- batched-affine pair levels -----------------------------------------------------------------
+// A bucket that holds m points needs m-1 additions whatever the order.  Adding the points of a
+// bucket PAIRWISE (level r+1 holds ceil(m_r / 2) partial sums per bucket) makes every addition an
+// affine + affine -> affine one, whose only expensive part is 1/(x2 - x1): all the denominators a
+// CTA handles are inverted together (Montgomery's trick: per-thread prefix products, a product
+// tree over the 128 thread totals in shared memory, ONE Fermat inversion per CTA), so an addition
+// costs 5 M + 1 S instead of the 8 M + 2 S of the XYZZ mixed addition.  After a few levels the
+// buckets are short and the remaining list goes through k_msm_accumulate<SRC = 1>.
+//
+// Level-r lists are sorted by bucket like the entry list; off_r = exclusive scan of the per-bucket
+// counts.  Output j of bucket b (local index jl) adds inputs off_r[b] + 2 jl and + 2 jl + 1; a
+// trailing odd element is passed through.
+
+__global__ void k_msm_level_counts(const uint32_t* offsets0, uint32_t nbuckets, uint32_t levels, uint32_t* cnt) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    uint32_t c = offsets0[b + 1] - offsets0[b];
+    for (uint32_t r = 0; r < levels; r++) {
+        c = (c + 1) >> 1;
+        cnt[(size_t)r * (nbuckets + 1) + b] = c;
+    }
+}
+
+static const uint32_t NO_PARTNER = 0xffffffffu;
+
+// One input of a pair level.  FIRST: `e` is an entry of the bucket-sorted list (table index, sign in
+// bit 31; (0,0) in the table = infinity).  Otherwise `e` is an index into the previous level's array
+// (infinity = all-ones top limb of x).
+template <class FQ, int FIRST>
+APB_D Fp<FQ> pair_load_x(const void* src, uint32_t e) {
+    return load_fp<FQ>(src, 2 * (uint64_t)(FIRST ? (e & 0x7fffffffu) : e));
+}
+template <class FQ, int FIRST>
+APB_D void pair_load_xy(const void* src, uint32_t e, Fp<FQ>& x, Fp<FQ>& y) {
+    load_affine<FQ>(src, FIRST ? (e & 0x7fffffffu) : e, x, y);
+}
+template <class FQ, int FIRST>
+APB_D bool pair_fix(uint32_t e, const Fp<FQ>& x, Fp<FQ>& y) {      // applies the sign, returns "is infinity"
+    if (FIRST) {
+        const bool inf = x.is_zero() && y.is_zero();
+        if (e >> 31) y = y.neg();
+        return inf;
+    }
+    return x.v[FQ::N - 1] == 0xffffffffu;
+}
+// rare path of the denominator pass: an operand at infinity, or equal x (doubling / inverse pair)
+template <class FQ, int FIRST>
+__device__ __noinline__ Fp<FQ> pair_den_special(const void* src, uint32_t e1, uint32_t e2) {
+    Fp<FQ> x1, y1, x2, y2;
+    pair_load_xy<FQ, FIRST>(src, e1, x1, y1);
+    pair_load_xy<FQ, FIRST>(src, e2, x2, y2);
+    const bool inf1 = pair_fix<FQ, FIRST>(e1, x1, y1), inf2 = pair_fix<FQ, FIRST>(e2, x2, y2);
+    if (inf1 || inf2) return Fp<FQ>::one();
+    if (x1 != x2) return x2 - x1;
+    if (y1 == y2 && !y1.is_zero()) return y1 + y1;       // doubling: lambda = 3 x^2 / 2 y
+    return Fp<FQ>::one();                                 // P + (-P) (or a 2-torsion point): infinity
+}
+
+// walks the outputs of a level in order and yields the ids of the (one or two) inputs each one adds
+struct PairWalker {
+    const uint32_t *off_in, *off_out;
+    uint32_t b, ipos, in_end;
+    uint64_t out_end;
+    APB_D void init(const uint32_t* oin, const uint32_t* oout, uint32_t nbuckets, uint64_t j) {
+        off_in = oin;
+        off_out = oout;
+        uint32_t lo = 0, hi = nbuckets;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid] <= j) lo = mid; else hi = mid;
+        }
+        b = lo;
+        while (off_out[b + 1] <= j) b++;
+        out_end = off_out[b + 1];
+        ipos = off_in[b] + 2 * (uint32_t)(j - off_out[b]);
+        in_end = off_in[b + 1];
+    }
+    template <int FIRST>
+    APB_D uint2 next(const uint32_t* entries, uint64_t j) {
+        if (j >= out_end) {
+            b++;
+            while (off_out[b + 1] <= j) b++;
+            out_end = off_out[b + 1];
+            ipos = off_in[b];
+            in_end = off_in[b + 1];
+        }
+        uint2 r;
+        const bool pair = ipos + 1 < in_end;
+        r.x = FIRST ? entries[ipos] : ipos;
+        r.y = pair ? (FIRST ? entries[ipos + 1] : ipos + 1) : NO_PARTNER;
+        ipos += pair ? 2 : 1;
+        return r;
+    }
+};
+
+// (No __syncwarp() in the loops: lanes whose range is shorter wait at the CTA barrier below, and a
+// warp-wide sync that names them would never complete.)
+// Both passes are software pipelined two deep (ids for output j+2 and the 96-byte records for j+1
+// are in flight while the multiplications of output j run): a thread's inputs are consecutive in the
+// level's list, but the table records behind the first level's ids are random 96-byte gathers.
+// Measured alternatives (B200, 2^18-point commits): no prefetch - same time; three CTAs per SM at 168
+// registers - slower (spills); two interleaved batches per thread for instruction-level
+// parallelism - slower (245 registers, no prefetch); a^(p-2) for the CTA's one inversion - the
+// single-lane dependent chain took 0.45 ms per launch, the binary Euclid inverse takes ~0.04 ms.
+template <class FQ, int FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_pairs(const uint32_t* entries, const void* src, const uint32_t* off_in,
+                                                         const uint32_t* off_out, uint32_t nbuckets, uint32_t E, void* dst,
+                                                         void* prefix, uint2* stash) {
+    typedef Fp<FQ> F;
+    __shared__ uint4 sm[256 * (FQ::N / 4)];              // product tree: node i at sm[i], leaves 128..255
+    const uint32_t tid = threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + tid;
+    const uint64_t Mout = off_out[nbuckets];
+    const uint64_t j0 = t * E < Mout ? t * E : Mout;
+    const uint64_t j1 = j0 + E < Mout ? j0 + E : Mout;
+
+    // pass 1 (forward): denominators and running prefix products; the ids each output reads are stashed
+    F run = F::one();
+    if (j0 < j1) {
+        PairWalker W;
+        W.init(off_in, off_out, nbuckets, j0);
+        uint2 cur = W.template next<FIRST>(entries, j0), nxt = make_uint2(0, NO_PARTNER);
+        F x1 = F::zero(), x2 = F::zero(), nx1 = F::zero(), nx2 = F::zero();
+        if (cur.y != NO_PARTNER) { x1 = pair_load_x<FQ, FIRST>(src, cur.x); x2 = pair_load_x<FQ, FIRST>(src, cur.y); }
+        if (j0 + 1 < j1) nxt = W.template next<FIRST>(entries, j0 + 1);
+        for (uint64_t j = j0; j < j1; j++) {
+            uint2 nn = make_uint2(0, NO_PARTNER);
+            if (j + 1 < j1 && nxt.y != NO_PARTNER) { nx1 = pair_load_x<FQ, FIRST>(src, nxt.x); nx2 = pair_load_x<FQ, FIRST>(src, nxt.y); }
+            if (j + 2 < j1) nn = W.template next<FIRST>(entries, j + 2);
+            stash[j] = cur;
+            store_fp<FQ>(prefix, j, run);
+            if (cur.y != NO_PARTNER) {
+                F d = x2 - x1;
+                const bool special = FIRST ? (x1.is_zero() || x2.is_zero() || d.is_zero())
+                                           : (x1.v[FQ::N - 1] == 0xffffffffu || x2.v[FQ::N - 1] == 0xffffffffu || d.is_zero());
+                if (special) d = pair_den_special<FQ, FIRST>(src, cur.x, cur.y);
+                run = run * d;
+            }
+            cur = nxt; nxt = nn; x1 = nx1; x2 = nx2;
+        }
+    }
+
+    // 1 / (this thread's product) through a product tree over the CTA and one inversion
+    store_fp<FQ>(sm, 128 + tid, run);
+    __syncthreads();
+    for (uint32_t s = 64; s >= 1; s >>= 1) {
+        if (tid < s) {
+            F a = load_fp<FQ>(sm, 2 * (s + tid)), c = load_fp<FQ>(sm, 2 * (s + tid) + 1);
+            store_fp<FQ>(sm, s + tid, a * c);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_fp<FQ>(sm, 1, load_fp<FQ>(sm, 1).inverse_binary());   // one thread: latency matters, not throughput
+    __syncthreads();
+    for (uint32_t s = 1; s <= 64; s <<= 1) {
+        if (tid < s) {
+            F inv = load_fp<FQ>(sm, s + tid);
+            F a = load_fp<FQ>(sm, 2 * (s + tid)), c = load_fp<FQ>(sm, 2 * (s + tid) + 1);
+            store_fp<FQ>(sm, 2 * (s + tid), inv * c);
+            store_fp<FQ>(sm, 2 * (s + tid) + 1, inv * a);
+        }
+        __syncthreads();
+    }
+    F rinv = load_fp<FQ>(sm, 128 + tid);
+
+    // pass 2 (backward): 1/d_j = rinv * prefix_j, then the affine addition
+    if (j0 < j1) {
+        uint2 cur = stash[j1 - 1], nxt = make_uint2(0, NO_PARTNER);
+        F x1, y1, x2 = F::zero(), y2 = F::zero(), pre = load_fp<FQ>(prefix, j1 - 1);
+        F nx1 = F::zero(), ny1 = F::zero(), nx2 = F::zero(), ny2 = F::zero(), npre = F::zero();
+        pair_load_xy<FQ, FIRST>(src, cur.x, x1, y1);
+        if (cur.y != NO_PARTNER) pair_load_xy<FQ, FIRST>(src, cur.y, x2, y2);
+        if (j1 - 1 > j0) nxt = stash[j1 - 2];
+        for (uint64_t j = j1; j-- > j0;) {
+            uint2 nn = make_uint2(0, NO_PARTNER);
+            if (j > j0) {
+                pair_load_xy<FQ, FIRST>(src, nxt.x, nx1, ny1);
+                if (nxt.y != NO_PARTNER) pair_load_xy<FQ, FIRST>(src, nxt.y, nx2, ny2);
+                npre = load_fp<FQ>(prefix, j - 1);
+            }
+            if (j > j0 + 1) nn = stash[j - 2];
+            bool inf1 = pair_fix<FQ, FIRST>(cur.x, x1, y1);
+            if (cur.y != NO_PARTNER) {
+                const bool inf2 = pair_fix<FQ, FIRST>(cur.y, x2, y2);
+                if (inf1 || inf2) {
+                    if (inf1) { x1 = x2; y1 = y2; inf1 = inf2; }
+                } else if (x1 != x2) {
+                    const F dinv = rinv * pre;
+                    rinv = rinv * (x2 - x1);
+                    const F lam = (y2 - y1) * dinv;
+                    const F x3 = lam.sqr() - x1 - x2;
+                    y1 = lam * (x1 - x3) - y1;
+                    x1 = x3;
+                } else if (y1 == y2 && !y1.is_zero()) {
+                    const F dinv = rinv * pre;
+                    rinv = rinv * (y1 + y1);
+                    const F xx = x1.sqr();
+                    const F lam = (xx + xx + xx) * dinv;
+                    const F x3 = lam.sqr() - x1 - x1;
+                    y1 = lam * (x1 - x3) - y1;
+                    x1 = x3;
+                } else {
+                    inf1 = true;
+                }
+            }
+            if (inf1) {
+                x1 = F::zero();
+                y1 = F::zero();
+                x1.v[FQ::N - 1] = 0xffffffffu;
+            }
+            store_fp<FQ>(dst, 2 * j, x1);
+            store_fp<FQ>(dst, 2 * j + 1, y1);
+            cur = nxt; nxt = nn; x1 = nx1; y1 = ny1; x2 = nx2; y2 = ny2; pre = npre;
+        }
+    }
+}
+
 // copies[f*n + i] = 2^(step*f) * P_i as affine points, f = 0..F-1 (copy 0 is the input itself)
 template <class FQ>
 __global__ void __launch_bounds__(128) k_ck_precompute(void* bases, uint64_t n, uint32_t F, uint32_t step) {
@@ -502,6 +723,11 @@ struct apb_ck_s {
     void *stage_a, *stage_b; size_t stage_cap;
     TreeJob* jobs; size_t jobs_cap;
     uint64_t* h_out; size_t h_out_cap;   // pinned
+    // batched-affine pair levels
+    uint32_t* lvl_words; size_t lvl_words_cap;      // per level: counts, offsets (nbuckets + 1 each)
+    void* lvl_pts[2]; size_t lvl_pts_cap[2];        // ping-pong arrays of affine partial sums
+    void* lvl_prefix; size_t lvl_prefix_cap;
+    uint2* lvl_stash; size_t lvl_stash_cap;
     // cached job table key
     uint32_t jobs_c, jobs_windows;
     std::vector<TreeJob>* h_jobs_a;
@@ -644,6 +870,7 @@ extern "C" void apb_ck_free(apb_ck_t ck) {
     cudaFree(ck->scan_tmp);
     cudaFree(ck->entries); cudaFree(ck->bucket_sums); cudaFree(ck->partials);
     cudaFree(ck->part_bucket); cudaFree(ck->stage_a); cudaFree(ck->jobs);
+    cudaFree(ck->lvl_words); cudaFree(ck->lvl_pts[0]); cudaFree(ck->lvl_pts[1]); cudaFree(ck->lvl_prefix); cudaFree(ck->lvl_stash);
     if (ck->h_out) cudaFreeHost(ck->h_out);
     delete ck->h_jobs_a;
     delete ck->h_jobs_b;
@@ -711,22 +938,48 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     const uint64_t Mmax = (uint64_t)total * g.W;
     if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
 
+    // batched-affine pair levels in front of the XYZZ accumulate: worth it when buckets are long
+    // (each level halves them) and the list is large enough to amortise one inversion per CTA
+    uint32_t levels = 0;
+    {
+        // measured on B200 (2^18-point commits, profiles/r01_msm_pair_levels.md): 2 levels for 2-4 polynomials
+        // per call, a third one pays from ~2^25 entries; the level arrays (152 B per first-level output)
+        // must fit a fixed HBM budget next to the resident table
+        uint32_t max_levels = Mmax >= ((uint64_t)1 << 25) ? 3 : 2;
+        uint64_t min_entries = (uint64_t)1 << 21, max_bytes = (uint64_t)32 << 30;
+        if (const char* e = getenv("APB_MSM_AFFINE_LEVELS")) max_levels = (uint32_t)atoi(e);
+        if (const char* e = getenv("APB_MSM_AFFINE_MIN")) min_entries = (uint64_t)atoll(e);
+        if (const char* e = getenv("APB_MSM_AFFINE_MAX_BYTES")) max_bytes = (uint64_t)atoll(e);
+        if (max_levels > 6) max_levels = 6;
+        const uint64_t need = (Mmax / 2 + nbuckets) * (96 + 48 + 8) + (Mmax / 4 + 2 * (uint64_t)nbuckets) * 96;
+        if (ck->radix == 32 && Mmax >= min_entries && Mmax < ((uint64_t)1 << 31) && need <= max_bytes) {
+            const uint64_t avg = Mmax / nbuckets;
+            while (levels < max_levels && (avg >> (levels + 1)) >= 8) levels++;
+        }
+    }
+    if (getenv("APB_MSM_DEBUG")) fprintf(stderr, "apb_msm: k=%u c=%u buckets=%u entries<=%llu pair levels=%u\n", B.k, g.c, nbuckets, (unsigned long long)Mmax, levels);
+    uint64_t U[8];                       // upper bounds of the list length per level
+    U[0] = Mmax;
+    for (uint32_t r = 0; r < levels; r++) U[r + 1] = U[r] / 2 + nbuckets;
+
     // chunk size for the accumulate pass: exactly one resident wave of threads
-    static int occupancy_known = 0, resident_blocks[1] = {2};
+    static int occupancy_known = 0, resident_blocks[2] = {2, 2};
     if (!occupancy_known) {
         occupancy_known = 1;
 #ifndef APB_EMU
         int nb = 0;
         if (ck->radix == 28) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate28<typename CV::FQ28, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
-        } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2, 0>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_pairs<FQ, 1, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
 #endif
     }
     uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[0] * 128;
-    uint32_t E = (uint32_t)((Mmax + target_threads - 1) / target_threads);
+    const uint64_t Macc = U[levels];
+    uint32_t E = (uint32_t)((Macc + target_threads - 1) / target_threads);
     if (E < 8) E = 8;
     if (const char* e = getenv("APB_MSM_CHUNK")) E = (uint32_t)atoi(e);
-    const uint64_t acc_threads = (Mmax + E - 1) / E;
+    const uint64_t acc_threads = (Macc + E - 1) / E;
     const uint64_t acc_blocks = (acc_threads + 127) / 128;
     const uint64_t acc_slots = acc_blocks * 128;
 
@@ -746,6 +999,14 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
             ck->part_bucket = nullptr;
             APB_CUDA_TRY(cudaMalloc((void**)&ck->part_bucket, ck->partial_cap / 192 * 4 + 64));
         }
+    }
+    const size_t lvl_stride = (size_t)nbuckets + 1;
+    if (levels) {
+        if ((rc = grow(&ck->lvl_words, &ck->lvl_words_cap, (size_t)levels * 2 * lvl_stride * 4)) != APB_OK) return rc;
+        if ((rc = grow(&ck->lvl_pts[0], &ck->lvl_pts_cap[0], (size_t)U[1] * 96)) != APB_OK) return rc;
+        if (levels > 1 && (rc = grow(&ck->lvl_pts[1], &ck->lvl_pts_cap[1], (size_t)U[2] * 96)) != APB_OK) return rc;
+        if ((rc = grow(&ck->lvl_prefix, &ck->lvl_prefix_cap, (size_t)U[1] * 48)) != APB_OK) return rc;
+        if ((rc = grow(&ck->lvl_stash, &ck->lvl_stash_cap, (size_t)U[1] * 8)) != APB_OK) return rc;
     }
     uint32_t a_bits, b_bits;
     const bool jobs_new = build_jobs(ck, g.c, windows, a_bits, b_bits);
@@ -792,18 +1053,50 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     }
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
     if (g_profile) cudaEventRecord(ev[1], g_stream);
-    // 4. accumulate  5. stitch
+    // 4. pair levels (batched-affine)  5. accumulate  6. stitch
+    const uint32_t* acc_offsets = ck->offsets;
+    if (levels) {
+        uint32_t* cnt = ck->lvl_words;
+        uint32_t* off = ck->lvl_words + (size_t)levels * lvl_stride;
+        APB_KLAUNCH(k_msm_level_counts, (nbuckets + 255) / 256, 256, 0, (const uint32_t*)ck->offsets, nbuckets, levels, cnt);
+        for (uint32_t r = 0; r < levels; r++) {
+            uint32_t* off_r = off + (size_t)r * lvl_stride;
+            int rc2 = u32_scan(cnt + (size_t)r * lvl_stride, off_r, nbuckets, ck->scan_tmp, off_r + nbuckets);
+            if (rc2 != APB_OK) return rc2;
+        }
+        const uint64_t pair_threads = (uint64_t)g_num_sms * resident_blocks[1] * 128;
+        auto k_pairs_first = k_msm_pairs<FQ, 1, 2>;
+        auto k_pairs_next = k_msm_pairs<FQ, 0, 2>;
+        for (uint32_t r = 0; r < levels; r++) {
+            uint32_t Ep = (uint32_t)((U[r + 1] + pair_threads - 1) / pair_threads);
+            if (Ep < 4) Ep = 4;
+            const unsigned blocks = (unsigned)(((U[r + 1] + Ep - 1) / Ep + 127) / 128);
+            const uint32_t* off_in = r == 0 ? ck->offsets : off + (size_t)(r - 1) * lvl_stride;
+            const uint32_t* off_out = off + (size_t)r * lvl_stride;
+            if (r == 0)
+                APB_KLAUNCH(k_pairs_first, blocks, 128, 0, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in, off_out, nbuckets, Ep,
+                            ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
+            else
+                APB_KLAUNCH(k_pairs_next, blocks, 128, 0, (const uint32_t*)nullptr, (const void*)ck->lvl_pts[(r - 1) & 1], off_in, off_out,
+                            nbuckets, Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, ck->lvl_stash);
+        }
+        acc_offsets = off + (size_t)(levels - 1) * lvl_stride;
+    }
     typedef typename CV::FQ28 FQ28;
     auto k_acc28 = k_msm_accumulate28<FQ28, 2>;
-    auto k_acc2 = k_msm_accumulate<FQ, 2>;
-    if (ck->radix == 28)
+    auto k_acc2 = k_msm_accumulate<FQ, 2, 0>;
+    auto k_acc_lvl = k_msm_accumulate<FQ, 2, 1>;
+    if (levels)
+        APB_KLAUNCH(k_acc_lvl, (unsigned)acc_blocks, 128, 0, (const uint32_t*)nullptr, acc_offsets, nbuckets,
+                    (const void*)ck->lvl_pts[(levels - 1) & 1], E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    else if (ck->radix == 28)
         APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                     (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     else
         APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                     (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[2], g_stream);
-    APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
+    APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, acc_offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
                 (const void*)ck->partials, (const int32_t*)ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[3], g_stream);
     // 6. bucket reduction trees

@@ -175,7 +175,8 @@ int apb_dev_sync(void);
 void* apb_stream(void);                     /* the cudaStream_t all work is enqueued on */
 
 /* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
-/* element-wise field op on the device: op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont, 5 sqr.
+/* element-wise field op on the device: op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont, 5 sqr,
+ * 6 inverse (0 -> 0).
  * field: 0 Fr381, 1 Fq381, 2 Fr377, 3 Fq377.  a, b, out: count x (4 or 6) u64. */
 int apb_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count);
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */

@@ -102,7 +102,9 @@ def prove_gadget_case(lib, curve_id: int, kind: str, tamper: bool = False):
     wires = gp.wires_to_mont(circ)
     if tamper:                                            # break one witness: the proof must be rejected
         wires = wires.copy()
-        wires[3, cs.n - 2] = wires[0, 1]
+        row = next(i for i, v in enumerate(cs.q_range) if v)
+        assert not np.array_equal(wires[0, row], wires[0, 1])
+        wires[0, row] = wires[0, 1]                       # a range accumulator replaced by a blinding value
     got = pr.prove(pk, wires, b"gadgets")
     pk.arena.close()
     ck.close()

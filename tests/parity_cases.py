@@ -45,6 +45,9 @@ def check_field_ops(lib, count=64, seed=1):
         assert enc.limbs_to_ints(lib.field_op(fid, 3, A, None)) == [x * f.R % f.p for x in a], f.name
         assert enc.limbs_to_ints(lib.field_op(fid, 4, A, None)) == [x * rinv % f.p for x in a], f.name
         assert enc.limbs_to_ints(lib.field_op(fid, 5, A, None)) == [x * x * rinv % f.p for x in a], f.name
+        # Montgomery inverse (binary extended Euclid): a = xR -> x^-1 R = a^-1 R^2; 0 -> 0
+        assert enc.limbs_to_ints(lib.field_op(fid, 6, A, None)) == \
+            [pow(x, -1, f.p) * f.R * f.R % f.p if x else 0 for x in a], f.name
 
 
 def check_ntt(lib, curve, log_n, in_len, seed=2, kinds=("fft", "ifft", "coset_fft", "coset_ifft")):

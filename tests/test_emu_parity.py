@@ -53,6 +53,25 @@ def test_msm_bls12_377_and_batch(emu_lib):
         pc.check_msm_progression(emu_lib, 0, 48, k=3)
 
 
+def test_msm_batched_affine_pair_levels(emu_lib):
+    """the batched-affine pair levels in front of the accumulate (narrow digits make buckets long enough
+    for 3 levels at these sizes): random, edge scalars, equal points / P + (-P) / infinity bases inside
+    a pair (doubling and cancellation branches), BLS12-377, batched commit, odd chunk sizes"""
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_C=4, APB_MSM_CHUNK=3):
+        pc.check_msm_tau(emu_lib, 0, 40)
+        pc.check_msm_tau(emu_lib, 0, 33, offset=3, montgomery=True)
+        for scal in ([0] * 20, [1] * 20, [pc.FR[0].p - 1] * 20, pc.edge_scalars(0, 20)):
+            pc.check_msm_tau(emu_lib, 0, 20, scalars=scal)
+        pc.check_msm_tau(emu_lib, 1, 30)
+        pc.check_msm_progression(emu_lib, 0, 48, k=3)
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_C=2, APB_MSM_CHUNK=5):
+        pc.check_msm_duplicates(emu_lib, 0)
+        pc.check_msm_duplicates(emu_lib, 1)
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_AFFINE_LEVELS=1, APB_MSM_C=4, APB_MSM_CHUNK=8):
+        pc.check_msm_tau(emu_lib, 0, 40)
+        pc.check_msm_duplicates(emu_lib, 0)
+
+
 def test_msm_windowed_geometry(emu_lib):
     """step = 64 bits per precomputed copy -> 4 effective windows folded on the host"""
     with pc.env(APB_MSM_STEP=64, APB_MSM_C=8, APB_MSM_CHUNK=16):
