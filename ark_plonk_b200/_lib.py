@@ -96,6 +96,8 @@ class Lib:
         c.apb_set_profiling.restype = None
         c.apb_msm_phase_ms.argtypes = [C.POINTER(C.c_double)]
         c.apb_msm_phase_ms.restype = None
+        c.apb_msm_work.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), ci]
+        c.apb_msm_work.restype = None
 
     # ------------------------------------------------------------------
     def check(self, rc: int):
@@ -116,6 +118,12 @@ class Lib:
 
     def set_profiling(self, on: bool):
         self.c.apb_set_profiling(1 if on else 0)
+
+    def msm_work(self, reset: bool = False):
+        """(model, issued) wide multiply-adds of the bucket accumulation stage while profiling"""
+        a, b = C.c_double(0), C.c_double(0)
+        self.c.apb_msm_work(C.byref(a), C.byref(b), 1 if reset else 0)
+        return a.value, b.value
 
     def msm_phase_ms(self):
         arr = (C.c_double * 4)()

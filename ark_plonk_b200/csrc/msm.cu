@@ -37,6 +37,8 @@ int g_num_sms = 1;
 int g_profile = 0;
 double g_acc_ms_total = 0.0;            // accumulated k_msm_accumulate time while profiling
 unsigned long long g_points_total = 0;  // scalars processed while profiling
+double g_madds_model = 0.0;             // while profiling: wide multiply-adds by the XYZZ cost model (entries x 10 x 300)
+double g_madds_issued = 0.0;            // ... and as issued: 6 x 300 per batched-affine pair addition, 10 x 300 per XYZZ one
 double g_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sort, accumulate, stitch, trees, copy+host epilogue
 
 static const int MAX_BATCH = 16;
@@ -946,7 +948,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         // per call, a third one pays from ~2^25 entries; the level arrays (152 B per first-level output)
         // must fit a fixed HBM budget next to the resident table
         uint32_t max_levels = Mmax >= ((uint64_t)1 << 25) ? 3 : 2;
-        uint64_t min_entries = (uint64_t)1 << 21, max_bytes = (uint64_t)32 << 30;
+        uint64_t min_entries = (uint64_t)6 << 20, max_bytes = (uint64_t)32 << 30;      // one 2^18-point MSM: no gain
         if (const char* e = getenv("APB_MSM_AFFINE_LEVELS")) max_levels = (uint32_t)atoi(e);
         if (const char* e = getenv("APB_MSM_AFFINE_MIN")) min_entries = (uint64_t)atoll(e);
         if (const char* e = getenv("APB_MSM_AFFINE_MAX_BYTES")) max_bytes = (uint64_t)atoll(e);
@@ -1116,6 +1118,12 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         }
         g_acc_ms_total += g_phase_ms[1];
         g_points_total += total;
+        {
+            double m = (double)Mmax, issued = 0.0;
+            for (uint32_t r = 0; r < levels; r++) { issued += (m / 2) * 1800.0; m /= 2; }
+            g_madds_model += (double)Mmax * 3000.0;
+            g_madds_issued += issued + m * 3000.0;
+        }
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
 
@@ -1265,6 +1273,11 @@ extern "C" void apb_msm_totals(double* accumulate_ms, unsigned long long* points
 }
 
 // host-side group addition of two normalised / Jacobian points (folding per-GPU partial sums)
+extern "C" void apb_msm_work(double* model_madds, double* issued_madds, int reset) {
+    if (model_madds) *model_madds = g_madds_model;
+    if (issued_madds) *issued_madds = g_madds_issued;
+    if (reset) { g_madds_model = 0.0; g_madds_issued = 0.0; }
+}
 extern "C" int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_xyz[18], uint64_t out_xyz[18]) {
     APB_API_LOCK();
     if (!a_xyz || !b_xyz || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_g1_add: null argument");

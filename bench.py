@@ -340,6 +340,7 @@ def run_b200(args):
         sampler = ClockSampler(local)
         sampler.start()
         lib.msm_totals(reset=True)
+        lib.msm_work(reset=True)
         launches0 = lib.kernel_launches()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -353,6 +354,7 @@ def run_b200(args):
         total_ms = e0.elapsed_time(e1) if split else max_over_ranks(e0.elapsed_time(e1))
         launches = lib.kernel_launches() - launches0
         acc_total_ms, pts_total = lib.msm_totals()
+        madds_model, madds_issued = lib.msm_work()
         clocks = sampler.result()
         ms_per_step = total_ms / K
         # end to end: pinned host witness in, proof bytes out
@@ -410,8 +412,14 @@ def run_b200(args):
                        "l2": "inputs exceed L2 (resident key table %d MB, prover key %d MB)" % ((n + 1) * 16 * 96 >> 20, pk.arena.elems * 32 >> 20),
                        "vs_baseline_note": "this value / published 20184 ms (Ryzen 7 3700X CPU, reference README.md:107); < 1 is faster"},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": len(proof) + 29 * 3024},
-            "roofline": {"kernel": "k_msm_accumulate", "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
+            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels) + k_msm_accumulate (XYZZ)",
+                         "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
                          "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": ncu_traffic("k_msm_accumulate"),
+                         "issued": {"achieved": madds_issued / (acc_total_ms * 1e-3) / 1e12,
+                                    "frac": madds_issued / (acc_total_ms * 1e-3) / wide_peak,
+                                    "issued_over_model": madds_issued / madds_model if madds_model else None,
+                                    "note": "multiply-adds actually issued: a batched-affine pair addition costs 6 Fq products, the XYZZ "
+                                            "mixed addition of the cost model 10; `achieved`/`frac` keep SURVEY 8(d)'s algorithmic figure"},
                          "traffic_note": "DRAM bytes per launch, mean of the 6 launches of one proof, ncu --set full (profiles/r01_ncu_prove_kernels.json); "
                                          "algorithmic bytes per launch = entries x (4 B id + 96 B point) = %.2e" % (pts_total / K * 16 * 100 / 6),
                          "kernel_ms_per_launch": acc_per_launch, "launches_per_step": 6,

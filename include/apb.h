@@ -191,6 +191,10 @@ void apb_set_profiling(int on);
 void apb_msm_phase_ms(double out[4]);
 /* totals since the last reset while profiling: k_msm_accumulate milliseconds and scalars processed */
 void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset);
+/* wide multiply-adds of the bucket accumulation stage since the last reset while profiling: by the
+ * XYZZ cost model of SURVEY 8(d) (entries x 10 Fq products x 300) and as issued (6 products per
+ * batched-affine pair addition, 10 per XYZZ mixed addition) */
+void apb_msm_work(double* model_madds, double* issued_madds, int reset);
 /* totals since the last reset while profiling: device milliseconds and number of transforms */
 void apb_ntt_totals(double* ms, unsigned long long* transforms, int reset);
 /* milliseconds of device time of the last blocking apb_msm / apb_ntt call (CUDA events) */
