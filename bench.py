@@ -92,14 +92,26 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def ncu_traffic(kernel_prefix: str):
-    """average DRAM bytes per launch of a kernel from the committed ncu capture (profiles/), or None"""
+def ncu_traffic(kernel_prefix: str, per: str | None = None, capture: str = "r01_ncu_prove_kernels.json"):
+    """average DRAM bytes per launch of the kernels matching `kernel_prefix` in a committed ncu capture
+    (profiles/), or None.  `per`: count one unit per launch of THAT kernel instead (a stage made of
+    several kernels: bytes of all matching kernels per launch of the stage's last kernel)."""
     try:
-        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_prove_kernels.json")))
+        rows = json.load(open(os.path.join(ROOT, "profiles", capture)))
     except Exception:
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, cnt = 0.0, 0
+    if per:
+        units = sum(1 for r in rows if per in r.get("Kernel Name", ""))
+        for r in rows:
+            if kernel_prefix not in r.get("Kernel Name", ""):
+                continue
+            for k, v in r.items():
+                if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+                    unit = k[k.index("[") + 1:-1] if "[" in k else "byte"
+                    tot += float(v) * scale.get(unit, 1.0)
+        return tot / units if units else None
     for r in rows:
         if kernel_prefix not in r.get("Kernel Name", ""):
             continue
@@ -414,14 +426,16 @@ def run_b200(args):
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": len(proof) + 29 * 3024},
             "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels) + k_msm_accumulate (XYZZ)",
                          "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
-                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": ncu_traffic("k_msm_accumulate"),
+                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": ncu_traffic("k_msm_", per="k_msm_accumulate", capture="r01_ncu_msm_stage.json"),
                          "issued": {"achieved": madds_issued / (acc_total_ms * 1e-3) / 1e12,
                                     "frac": madds_issued / (acc_total_ms * 1e-3) / wide_peak,
                                     "issued_over_model": madds_issued / madds_model if madds_model else None,
                                     "note": "multiply-adds actually issued: a batched-affine pair addition costs 6 Fq products, the XYZZ "
                                             "mixed addition of the cost model 10; `achieved`/`frac` keep SURVEY 8(d)'s algorithmic figure"},
-                         "traffic_note": "DRAM bytes per launch, mean of the 6 launches of one proof, ncu --set full (profiles/r01_ncu_prove_kernels.json); "
-                                         "algorithmic bytes per launch = entries x (4 B id + 96 B point) = %.2e" % (pts_total / K * 16 * 100 / 6),
+                         "traffic_note": "DRAM bytes of the stage (pair levels + accumulate) per commit call, mean of the 6 calls of one proof, "
+                                         "ncu --set full (profiles/r01_ncu_msm_stage.json); algorithmic bytes per call = entries x (4 B id + "
+                                         "96 B point) = %.2e; the pair levels add per first-level output 2 x 48 B (x re-read), 48 B prefix "
+                                         "(written + read), 8 B ids (written + read) and 96 B partial sum (written + read)" % (pts_total / K * 16 * 100 / 6),
                          "kernel_ms_per_launch": acc_per_launch, "launches_per_step": 6,
                          "kernel_share_of_step": acc_total_ms / K / ms_per_step,
                          "frac_in_32bit_imad_units": 2 * achieved / (imad32_peak / 1e12),
