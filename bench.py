@@ -29,6 +29,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: keep NCCL's version / debug banner on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
