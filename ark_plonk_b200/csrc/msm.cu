@@ -506,8 +506,8 @@ struct PairWalker {
 
 // (No __syncwarp() in the loops: lanes whose range is shorter wait at the CTA barrier below, and a
 // warp-wide sync that names them would never complete.)
-// Both passes are software pipelined two deep (ids for output j+2 and the 96-byte records for j+1
-// are in flight while the multiplications of output j run): a thread's inputs are consecutive in the
+// Pass 2 is software pipelined two deep (ids for output j-2 and the 96-byte records for j-1 are in
+// flight while the multiplications of output j run): a thread's inputs are consecutive in the
 // level's list, but the table records behind the first level's ids are random 96-byte gathers.
 // Measured alternatives (B200, 2^18-point commits): no prefetch - same time; three CTAs per SM at 168
 // registers - slower (spills); two interleaved batches per thread for instruction-level
@@ -525,29 +525,39 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs(const uint32_t* entries
     const uint64_t j0 = t * E < Mout ? t * E : Mout;
     const uint64_t j1 = j0 + E < Mout ? j0 + E : Mout;
 
-    // pass 1 (forward): denominators and running prefix products; the ids each output reads are stashed
+    // pass 1 (forward): denominators and running prefix products; the ids each output reads are stashed.
+    // One multiplication per output is too short to hide a gather behind, so outputs go in groups of
+    // four: 8 ids, then 8 x-coordinates in flight together, then the 4 dependent products.
     F run = F::one();
     if (j0 < j1) {
         PairWalker W;
         W.init(off_in, off_out, nbuckets, j0);
-        uint2 cur = W.template next<FIRST>(entries, j0), nxt = make_uint2(0, NO_PARTNER);
-        F x1 = F::zero(), x2 = F::zero(), nx1 = F::zero(), nx2 = F::zero();
-        if (cur.y != NO_PARTNER) { x1 = pair_load_x<FQ, FIRST>(src, cur.x); x2 = pair_load_x<FQ, FIRST>(src, cur.y); }
-        if (j0 + 1 < j1) nxt = W.template next<FIRST>(entries, j0 + 1);
-        for (uint64_t j = j0; j < j1; j++) {
-            uint2 nn = make_uint2(0, NO_PARTNER);
-            if (j + 1 < j1 && nxt.y != NO_PARTNER) { nx1 = pair_load_x<FQ, FIRST>(src, nxt.x); nx2 = pair_load_x<FQ, FIRST>(src, nxt.y); }
-            if (j + 2 < j1) nn = W.template next<FIRST>(entries, j + 2);
-            stash[j] = cur;
-            store_fp<FQ>(prefix, j, run);
-            if (cur.y != NO_PARTNER) {
-                F d = x2 - x1;
-                const bool special = FIRST ? (x1.is_zero() || x2.is_zero() || d.is_zero())
-                                           : (x1.v[FQ::N - 1] == 0xffffffffu || x2.v[FQ::N - 1] == 0xffffffffu || d.is_zero());
-                if (special) d = pair_den_special<FQ, FIRST>(src, cur.x, cur.y);
-                run = run * d;
+        for (uint64_t j = j0; j < j1; j += 4) {
+            uint2 id[4];
+            F xa[4], xb[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) id[q] = j + q < j1 ? W.template next<FIRST>(entries, j + q) : make_uint2(0, NO_PARTNER);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (id[q].y != NO_PARTNER) {
+                    xa[q] = pair_load_x<FQ, FIRST>(src, id[q].x);
+                    xb[q] = pair_load_x<FQ, FIRST>(src, id[q].y);
+                }
             }
-            cur = nxt; nxt = nn; x1 = nx1; x2 = nx2;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (j + q < j1) {
+                    stash[j + q] = id[q];
+                    store_fp<FQ>(prefix, j + q, run);
+                    if (id[q].y != NO_PARTNER) {
+                        F d = xb[q] - xa[q];
+                        const bool special = FIRST ? (xa[q].is_zero() || xb[q].is_zero() || d.is_zero())
+                                                   : (xa[q].v[FQ::N - 1] == 0xffffffffu || xb[q].v[FQ::N - 1] == 0xffffffffu || d.is_zero());
+                        if (special) d = pair_den_special<FQ, FIRST>(src, id[q].x, id[q].y);
+                        run = run * d;
+                    }
+                }
+            }
         }
     }
 

@@ -62,6 +62,20 @@ def test_msm_duplicate_points_and_cancellation(gpu_lib):
         pc.check_msm_tau(gpu_lib, 0, 3000)
 
 
+@pytest.mark.parametrize("curve", [0, 1])
+def test_msm_batched_affine_pair_levels(gpu_lib, curve):
+    """the pair levels (default from 6 M bucket entries; forced here) on both curves: closed-form KAT with a
+    ragged 3-polynomial batch, edge scalars, and equal points / P + (-P) / infinity inside a pair"""
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_AFFINE_LEVELS=3):
+        pc.check_msm_progression(gpu_lib, curve, 1 << 15, k=3)
+        pc.check_msm_tau(gpu_lib, curve, 5000, scalars=pc.edge_scalars(curve, 5000))
+        pc.check_msm_tau(gpu_lib, curve, 3000, scalars=[1] * 3000)
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_C=2):
+        pc.check_msm_duplicates(gpu_lib, curve)
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_AFFINE_LEVELS=1, APB_MSM_C=4):
+        pc.check_msm_duplicates(gpu_lib, curve)
+
+
 def test_msm_windowed_geometry(gpu_lib):
     with pc.env(APB_MSM_STEP=64):
         pc.check_msm_tau(gpu_lib, 0, 3000)
