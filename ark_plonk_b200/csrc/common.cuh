@@ -59,6 +59,29 @@ APB_D Fp<P> load_fp(const void* base, size_t idx) {
     }
     return r;
 }
+// Same load as an `asm volatile` statement: it keeps its program position relative to the (volatile)
+// multiply-add chains, so a prefetch written at the top of a loop body is ISSUED there.  (A plain
+// load whose value is only consumed at the bottom gets sunk to the bottom by the compiler under
+// register pressure, and the software pipeline silently disappears.)  NC: read-only data path.
+template <class P, int NC>
+APB_D Fp<P> load_fp_early(const void* base, size_t idx) {
+#ifdef __CUDA_ARCH__
+    Fp<P> r;
+    const uint4* p = reinterpret_cast<const uint4*>(base) + idx * (P::N / 4);
+#pragma unroll
+    for (int i = 0; i < P::N / 4; i++) {
+        if (NC)
+            asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r.v[4 * i]), "=r"(r.v[4 * i + 1]), "=r"(r.v[4 * i + 2]), "=r"(r.v[4 * i + 3]) : "l"(p + i));
+        else
+            asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r.v[4 * i]), "=r"(r.v[4 * i + 1]), "=r"(r.v[4 * i + 2]), "=r"(r.v[4 * i + 3]) : "l"(p + i) : "memory");
+    }
+    return r;
+#else
+    return load_fp<P>(base, idx);
+#endif
+}
 template <class P>
 APB_D void store_fp(void* base, size_t idx, const Fp<P>& a) {
     uint4* p = reinterpret_cast<uint4*>(base) + idx * (P::N / 4);

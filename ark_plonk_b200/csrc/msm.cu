@@ -439,11 +439,13 @@ static const uint32_t NO_PARTNER = 0xffffffffu;
 // (infinity = all-ones top limb of x).
 template <class FQ, int FIRST>
 APB_D Fp<FQ> pair_load_x(const void* src, uint32_t e) {
-    return load_fp<FQ>(src, 2 * (uint64_t)(FIRST ? (e & 0x7fffffffu) : e));
+    return load_fp_early<FQ, 1>(src, 2 * (uint64_t)(FIRST ? (e & 0x7fffffffu) : e));
 }
 template <class FQ, int FIRST>
 APB_D void pair_load_xy(const void* src, uint32_t e, Fp<FQ>& x, Fp<FQ>& y) {
-    load_affine<FQ>(src, FIRST ? (e & 0x7fffffffu) : e, x, y);
+    const uint64_t idx = FIRST ? (e & 0x7fffffffu) : e;
+    x = load_fp_early<FQ, 1>(src, 2 * idx);
+    y = load_fp_early<FQ, 1>(src, 2 * idx + 1);
 }
 template <class FQ, int FIRST>
 APB_D bool pair_fix(uint32_t e, const Fp<FQ>& x, Fp<FQ>& y) {      // applies the sign, returns "is infinity"
@@ -453,6 +455,15 @@ APB_D bool pair_fix(uint32_t e, const Fp<FQ>& x, Fp<FQ>& y) {      // applies th
         return inf;
     }
     return x.v[FQ::N - 1] == 0xffffffffu;
+}
+APB_D uint2 load_u2_early(const uint2* p) {      // see load_fp_early: keeps its position among the volatile chains
+#ifdef __CUDA_ARCH__
+    uint2 r;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+#else
+    return *p;
+#endif
 }
 // rare path of the denominator pass: an operand at infinity, or equal x (doubling / inverse pair)
 template <class FQ, int FIRST>
@@ -597,9 +608,9 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs(const uint32_t* entries
             if (j > j0) {
                 pair_load_xy<FQ, FIRST>(src, nxt.x, nx1, ny1);
                 if (nxt.y != NO_PARTNER) pair_load_xy<FQ, FIRST>(src, nxt.y, nx2, ny2);
-                npre = load_fp<FQ>(prefix, j - 1);
+                npre = load_fp_early<FQ, 0>(prefix, j - 1);
             }
-            if (j > j0 + 1) nn = stash[j - 2];
+            if (j > j0 + 1) nn = load_u2_early(stash + (j - 2));
             bool inf1 = pair_fix<FQ, FIRST>(cur.x, x1, y1);
             if (cur.y != NO_PARTNER) {
                 const bool inf2 = pair_fix<FQ, FIRST>(cur.y, x2, y2);
