@@ -13,8 +13,11 @@
 //     G = 1 all 16 digit positions share ONE bucket set and no window doublings remain.
 //   * digits -> histogram -> exclusive scan -> scatter gives the (bucket, point) pairs sorted
 //     by bucket (a counting sort; keys are bucket ids).
-//   * accumulation walks the sorted list in equal chunks per thread (perfect balance for any
-//     scalar distribution); runs that cross chunk borders are stitched by a second kernel.
+//   * large lists first go through batched-affine PAIR LEVELS (k_msm_pairs): the points of every
+//     bucket are added pairwise as affine points with all denominators of a CTA inverted together
+//     (5M+1S per addition instead of 8M+2S), two or three times, which halves the list each time.
+//   * accumulation walks the (remaining) sorted list in equal chunks per thread (perfect balance
+//     for any scalar distribution); runs that cross chunk borders are stitched by a second kernel.
 //   * the weighted bucket sum  sum_b (b+1) * S_b  is evaluated with log-depth trees only:
 //     buckets are viewed as a 2^a x 2^b matrix, row/column sums are trees, and the two small
 //     weighted sums are split by weight bit (V_k = sum of entries whose weight has bit k set).
