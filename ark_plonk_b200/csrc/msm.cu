@@ -966,7 +966,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
 
     // batched-affine pair levels in front of the XYZZ accumulate: worth it when buckets are long
     // (each level halves them) and the list is large enough to amortise one inversion per CTA
-    uint32_t levels = 0;
+    uint32_t levels = 0, slices = 1;
     {
         // measured on B200 (2^18-point commits, profiles/r01_msm_pair_levels.md): 2 levels for 2-4 polynomials
         // per call, a third one pays from ~2^25 entries; the level arrays (152 B per first-level output)
@@ -978,15 +978,30 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if (const char* e = getenv("APB_MSM_AFFINE_MAX_BYTES")) max_bytes = (uint64_t)atoll(e);
         if (max_levels > 6) max_levels = 6;
         const uint64_t need = (Mmax / 2 + nbuckets) * (96 + 48 + 8) + (Mmax / 4 + 2 * (uint64_t)nbuckets) * 96;
-        if (ck->radix == 32 && Mmax >= min_entries && Mmax < ((uint64_t)1 << 31) && need <= max_bytes) {
+        bool want = ck->radix == 32 && Mmax >= min_entries && Mmax < ((uint64_t)1 << 31);
+        if (want && need > max_bytes) {
+            // too large for the budget in one piece: run the stage over equal BUCKET RANGES one after the other
+            // (the list is sorted by bucket, so a range of buckets is a contiguous piece of it)
+            want = false;
+            for (uint32_t S = 2; S <= 64 && nbuckets % S == 0 && nbuckets / S >= 8; S *= 2) {
+                const uint64_t Mb = Mmax / S + Mmax / S / 4 + 1024, nbS = nbuckets / S;
+                if ((Mb / 2 + nbS) * (96 + 48 + 8) + (Mb / 4 + 2 * nbS) * 96 <= max_bytes) { slices = S; want = true; break; }
+            }
+        }
+        if (want) {
             const uint64_t avg = Mmax / nbuckets;
             while (levels < max_levels && (avg >> (levels + 1)) >= 8) levels++;
         }
+        if (!levels) slices = 1;
     }
-    if (getenv("APB_MSM_DEBUG")) fprintf(stderr, "apb_msm: k=%u c=%u buckets=%u entries<=%llu pair levels=%u\n", B.k, g.c, nbuckets, (unsigned long long)Mmax, levels);
-    uint64_t U[8];                       // upper bounds of the list length per level
-    U[0] = Mmax;
-    for (uint32_t r = 0; r < levels; r++) U[r + 1] = U[r] / 2 + nbuckets;
+    if (getenv("APB_MSM_DEBUG")) fprintf(stderr, "apb_msm: k=%u c=%u buckets=%u entries<=%llu pair levels=%u slices=%u\n", B.k, g.c, nbuckets, (unsigned long long)Mmax, levels, slices);
+    const uint32_t nbS = nbuckets / slices;                     // buckets per slice
+    // entries per slice: exact sizes are read back after the sort; a slice above this bound (skewed
+    // scalars) makes the whole call fall back to the plain accumulate
+    const uint64_t Mslice = slices == 1 ? Mmax : Mmax / slices + Mmax / slices / 4 + 1024;
+    uint64_t U[8];                       // upper bounds of the list length per level (per slice)
+    U[0] = Mslice;
+    for (uint32_t r = 0; r < levels; r++) U[r + 1] = U[r] / 2 + nbS;
 
     // chunk size for the accumulate pass: exactly one resident wave of threads
     static int occupancy_known = 0, resident_blocks[2] = {2, 2};
@@ -1008,6 +1023,11 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     const uint64_t acc_threads = (Macc + E - 1) / E;
     const uint64_t acc_blocks = (acc_threads + 127) / 128;
     const uint64_t acc_slots = acc_blocks * 128;
+    // plan B (only for a sliced call whose slices turn out unbalanced): plain accumulate over the whole list
+    uint32_t E_fb = (uint32_t)((Mmax + target_threads - 1) / target_threads);
+    if (E_fb < 8) E_fb = 8;
+    const uint64_t fb_blocks = ((Mmax + E_fb - 1) / E_fb + 127) / 128;
+    const uint64_t slots_alloc = slices > 1 ? std::max<uint64_t>(acc_slots, fb_blocks * 128) : acc_slots;
 
     int rc;
     if ((rc = grow(&ck->counts, &ck->buckets_cap, (size_t)(nbuckets + 1) * 4 * 3)) != APB_OK) return rc;
@@ -1017,7 +1037,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     if ((rc = grow(&ck->entries, &ck->entries_cap, (size_t)Mmax * 4)) != APB_OK) return rc;
     if ((rc = grow(&ck->bucket_sums, &ck->sums_cap, (size_t)nbuckets * 192)) != APB_OK) return rc;
     {
-        size_t need = acc_slots * 2 * 192;
+        size_t need = slots_alloc * 2 * 192;
         size_t cap2 = ck->partial_cap;
         if ((rc = grow(&ck->partials, &ck->partial_cap, need)) != APB_OK) return rc;
         if (cap2 != ck->partial_cap) {
@@ -1026,7 +1046,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
             APB_CUDA_TRY(cudaMalloc((void**)&ck->part_bucket, ck->partial_cap / 192 * 4 + 64));
         }
     }
-    const size_t lvl_stride = (size_t)nbuckets + 1;
+    const size_t lvl_stride = (size_t)nbS + 1;
     if (levels) {
         if ((rc = grow(&ck->lvl_words, &ck->lvl_words_cap, (size_t)levels * 2 * lvl_stride * 4)) != APB_OK) return rc;
         if ((rc = grow(&ck->lvl_pts[0], &ck->lvl_pts_cap[0], (size_t)U[1] * 96)) != APB_OK) return rc;
@@ -1079,51 +1099,83 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     }
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
     if (g_profile) cudaEventRecord(ev[1], g_stream);
-    // 4. pair levels (batched-affine)  5. accumulate  6. stitch
-    const uint32_t* acc_offsets = ck->offsets;
-    if (levels) {
-        uint32_t* cnt = ck->lvl_words;
-        uint32_t* off = ck->lvl_words + (size_t)levels * lvl_stride;
-        APB_KLAUNCH(k_msm_level_counts, (nbuckets + 255) / 256, 256, 0, (const uint32_t*)ck->offsets, nbuckets, levels, cnt);
-        for (uint32_t r = 0; r < levels; r++) {
-            uint32_t* off_r = off + (size_t)r * lvl_stride;
-            int rc2 = u32_scan(cnt + (size_t)r * lvl_stride, off_r, nbuckets, ck->scan_tmp, off_r + nbuckets);
-            if (rc2 != APB_OK) return rc2;
-        }
-        const uint64_t pair_threads = (uint64_t)g_num_sms * resident_blocks[1] * 128;
-        auto k_pairs_first = k_msm_pairs<FQ, 1, 2>;
-        auto k_pairs_next = k_msm_pairs<FQ, 0, 2>;
-        for (uint32_t r = 0; r < levels; r++) {
-            uint32_t Ep = (uint32_t)((U[r + 1] + pair_threads - 1) / pair_threads);
-            if (Ep < 4) Ep = 4;
-            const unsigned blocks = (unsigned)(((U[r + 1] + Ep - 1) / Ep + 127) / 128);
-            const uint32_t* off_in = r == 0 ? ck->offsets : off + (size_t)(r - 1) * lvl_stride;
-            const uint32_t* off_out = off + (size_t)r * lvl_stride;
-            if (r == 0)
-                APB_KLAUNCH(k_pairs_first, blocks, 128, 0, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in, off_out, nbuckets, Ep,
-                            ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
-            else
-                APB_KLAUNCH(k_pairs_next, blocks, 128, 0, (const uint32_t*)nullptr, (const void*)ck->lvl_pts[(r - 1) & 1], off_in, off_out,
-                            nbuckets, Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, ck->lvl_stash);
-        }
-        acc_offsets = off + (size_t)(levels - 1) * lvl_stride;
-    }
+    // 4. pair levels (batched-affine)  5. accumulate  6. stitch - over the whole bucket range, or slice by slice
     typedef typename CV::FQ28 FQ28;
     auto k_acc28 = k_msm_accumulate28<FQ28, 2>;
     auto k_acc2 = k_msm_accumulate<FQ, 2, 0>;
     auto k_acc_lvl = k_msm_accumulate<FQ, 2, 1>;
-    if (levels)
-        APB_KLAUNCH(k_acc_lvl, (unsigned)acc_blocks, 128, 0, (const uint32_t*)nullptr, acc_offsets, nbuckets,
-                    (const void*)ck->lvl_pts[(levels - 1) & 1], E, ck->bucket_sums, ck->partials, ck->part_bucket);
-    else if (ck->radix == 28)
-        APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
-                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
-    else
-        APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
-                    (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+    auto k_pairs_first = k_msm_pairs<FQ, 1, 2>;
+    auto k_pairs_next = k_msm_pairs<FQ, 0, 2>;
+    bool unbalanced = false;
+    std::vector<uint32_t> bound(slices + 1);
+    if (slices > 1) {
+        for (uint32_t sl = 0; sl <= slices; sl++)
+            APB_CUDA_TRY(cudaMemcpyAsync(&bound[sl], ck->offsets + (size_t)sl * nbS, 4, cudaMemcpyDeviceToHost, g_stream));
+        APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+        for (uint32_t sl = 0; sl < slices; sl++) unbalanced = unbalanced || (uint64_t)(bound[sl + 1] - bound[sl]) > Mslice;
+    }
+    if (unbalanced) {
+        if (getenv("APB_MSM_DEBUG")) fprintf(stderr, "apb_msm: unbalanced slices, plain accumulate\n");
+        APB_KLAUNCH(k_acc2, (unsigned)fb_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                    (const void*)ck->bases, E_fb, ck->bucket_sums, ck->partials, ck->part_bucket);
+        APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)fb_blocks, 128, 0, (const uint32_t*)ck->offsets, E_fb, (uint64_t)(fb_blocks * 128), ck->bucket_sums,
+                    (const void*)ck->partials, (const int32_t*)ck->part_bucket);
+    }
+    for (uint32_t sl = 0; sl < slices && !unbalanced; sl++) {
+        const uint32_t* offsets0 = ck->offsets + (size_t)sl * nbS;          // absolute positions in the entry list
+        void* sums = (char*)ck->bucket_sums + (size_t)sl * nbS * 192;
+        const uint32_t* acc_offsets = offsets0;
+        // grids from the exact size of a slice (the bounds U[] above size the workspace)
+        uint64_t Ue[8];
+        uint32_t Es = E;
+        uint64_t blocks_s = acc_blocks;
+        for (uint32_t r = 0; r <= levels; r++) Ue[r] = U[r];
+        if (slices > 1) {
+            Ue[0] = bound[sl + 1] - bound[sl];
+            for (uint32_t r = 0; r < levels; r++) Ue[r + 1] = Ue[r] / 2 + nbS;
+            Es = (uint32_t)((Ue[levels] + target_threads - 1) / target_threads);
+            if (Es < 8) Es = 8;
+            blocks_s = ((Ue[levels] + Es - 1) / Es + 127) / 128;
+            if (blocks_s > slots_alloc / 128) { blocks_s = slots_alloc / 128; Es = (uint32_t)((Ue[levels] + blocks_s * 128 - 1) / (blocks_s * 128)); }
+        }
+        if (levels) {
+            uint32_t* cnt = ck->lvl_words;
+            uint32_t* off = ck->lvl_words + (size_t)levels * lvl_stride;
+            APB_KLAUNCH(k_msm_level_counts, (nbS + 255) / 256, 256, 0, offsets0, nbS, levels, cnt);
+            for (uint32_t r = 0; r < levels; r++) {
+                uint32_t* off_r = off + (size_t)r * lvl_stride;
+                int rc2 = u32_scan(cnt + (size_t)r * lvl_stride, off_r, nbS, ck->scan_tmp, off_r + nbS);
+                if (rc2 != APB_OK) return rc2;
+            }
+            const uint64_t pair_threads = (uint64_t)g_num_sms * resident_blocks[1] * 128;
+            for (uint32_t r = 0; r < levels; r++) {
+                uint32_t Ep = (uint32_t)((Ue[r + 1] + pair_threads - 1) / pair_threads);
+                if (Ep < 4) Ep = 4;
+                const unsigned blocks = (unsigned)(((Ue[r + 1] + Ep - 1) / Ep + 127) / 128);
+                const uint32_t* off_in = r == 0 ? offsets0 : off + (size_t)(r - 1) * lvl_stride;
+                const uint32_t* off_out = off + (size_t)r * lvl_stride;
+                if (r == 0)
+                    APB_KLAUNCH(k_pairs_first, blocks, 128, 0, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in, off_out, nbS, Ep,
+                                ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
+                else
+                    APB_KLAUNCH(k_pairs_next, blocks, 128, 0, (const uint32_t*)nullptr, (const void*)ck->lvl_pts[(r - 1) & 1], off_in, off_out,
+                                nbS, Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, ck->lvl_stash);
+            }
+            acc_offsets = off + (size_t)(levels - 1) * lvl_stride;          // slice-relative from here on
+        }
+        if (levels)
+            APB_KLAUNCH(k_acc_lvl, (unsigned)blocks_s, 128, 0, (const uint32_t*)nullptr, acc_offsets, nbS,
+                        (const void*)ck->lvl_pts[(levels - 1) & 1], Es, sums, ck->partials, ck->part_bucket);
+        else if (ck->radix == 28)
+            APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                        (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+        else
+            APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
+                        (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
+        APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)blocks_s, 128, 0, acc_offsets, Es, (uint64_t)(blocks_s * 128), sums,
+                    (const void*)ck->partials, (const int32_t*)ck->part_bucket);
+    }
     if (g_profile) cudaEventRecord(ev[2], g_stream);
-    APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)acc_blocks, 128, 0, acc_offsets, E, (uint64_t)acc_slots, ck->bucket_sums,
-                (const void*)ck->partials, (const int32_t*)ck->part_bucket);
     if (g_profile) cudaEventRecord(ev[3], g_stream);
     // 6. bucket reduction trees
     APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)((njobs_a + 3) / 4), 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs,

@@ -72,6 +72,25 @@ def test_msm_batched_affine_pair_levels(emu_lib):
         pc.check_msm_duplicates(emu_lib, 0)
 
 
+def test_msm_pair_levels_sliced_by_bucket_range(emu_lib):
+    """a level workspace above the HBM budget: the stage runs over bucket ranges one after the other; a skewed
+    digit distribution (every entry in one bucket) falls back to the plain accumulate"""
+    import os
+    seen = []
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_C=4, APB_MSM_CHUNK=3, APB_MSM_AFFINE_MAX_BYTES=190000):
+        pc.check_msm_tau(emu_lib, 0, 40)
+        pc.check_msm_tau(emu_lib, 1, 40)
+        pc.check_msm_tau(emu_lib, 0, 40, scalars=[1] * 40)                     # unbalanced slices
+        pc.check_msm_tau(emu_lib, 0, 40, scalars=pc.edge_scalars(0, 40))
+        pc.check_msm_duplicates(emu_lib, 0)
+        pc.check_msm_progression(emu_lib, 0, 48, k=2)
+    with pc.env(APB_MSM_AFFINE_MIN=0, APB_MSM_C=8, APB_MSM_CHUNK=7, APB_MSM_AFFINE_MAX_BYTES=250000):
+        same_digits = int("01" * 31, 16)                                       # every 8-bit digit is 1: two buckets hold everything
+        pc.check_msm_tau(emu_lib, 0, 200, scalars=[same_digits] * 200)         # 8 slices, unbalanced -> fallback
+        pc.check_msm_tau(emu_lib, 0, 200)                                      # 8 slices, balanced
+    assert not seen and "APB_MSM_AFFINE_MAX_BYTES" not in os.environ
+
+
 def test_msm_windowed_geometry(emu_lib):
     """step = 64 bits per precomputed copy -> 4 effective windows folded on the host"""
     with pc.env(APB_MSM_STEP=64, APB_MSM_C=8, APB_MSM_CHUNK=16):

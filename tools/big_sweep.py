@@ -15,10 +15,11 @@ out = {"imad_wide_per_s": wide, "msm": [], "ntt": []}
 stream = torch.cuda.ExternalStream(lib.c.apb_stream())
 max_msm = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 max_ntt = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+min_msm = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 lib.set_profiling(True)
 for curve in (0, 1):
     for log_n in ([16, 18, 20, 22, 24, 26] if curve == 0 else [18, 22]):
-        if log_n > max_msm: continue
+        if log_n > max_msm or log_n < min_msm: continue
         n = 1 << log_n
         tau = 0xABCDEF0123456789ABCDEF + curve
         t0 = time.time(); ck = kzg.CommitterKey.from_tau(curve, tau, n); t_setup = time.time() - t0
