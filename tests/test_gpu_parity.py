@@ -196,6 +196,7 @@ def test_ntt_roundtrip_on_device_large(gpu_lib, log_n):
     d = Radix2EvaluationDomain(0, n, lib=gpu_lib)
     x = torch.randint(0, 2 ** 60, (n, 4), dtype=torch.int64, device="cuda")
     y = torch.empty_like(x)
+    torch.cuda.synchronize()        # x is filled on torch's stream; the library transforms on its own stream
     for fwd, inv in ((2, 3), (0, 1)):
         d.ntt_dev(fwd, x.data_ptr(), n, y.data_ptr(), sync=True)
         assert not torch.equal(x[:1024], y[:1024])

@@ -49,6 +49,7 @@ for curve in (0, 1):
         n = 1 << log_n
         d = Radix2EvaluationDomain(curve, n)
         x = torch.randint(0, 2**60, (n, 4), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()        # filled on torch's stream; the library uses its own
         y = torch.empty_like(x)
         rec = dict(curve=curve, log_n=log_n)
         for kind, name in ((0, "fft"), (2, "coset_fft")):

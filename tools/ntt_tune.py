@@ -13,7 +13,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for log_n in (18, 20, 24):
         n = 1 << log_n
         d = Radix2EvaluationDomain(0, n)
-        x = torch.randint(0, 2**60, (n, 4), dtype=torch.int64, device="cuda"); y = torch.empty_like(x)
+        x = torch.randint(0, 2**60, (n, 4), dtype=torch.int64, device="cuda"); y = torch.empty_like(x); torch.cuda.synchronize()
         for _ in range(3): d.ntt_dev(0, x.data_ptr(), n, y.data_ptr(), sync=True)
         ts = []
         for _ in range(7):

@@ -29,6 +29,7 @@ print("msm ms", lib.last_device_ms())
 N = 1 << log_ntt
 d = Radix2EvaluationDomain(0, N)
 x = torch.randint(0, 2**62, (N, 4), dtype=torch.int64, device="cuda")
+torch.cuda.synchronize()        # filled on torch's stream; the library uses its own
 y = torch.empty_like(x)
 for _ in range(3):
     d.ntt_dev(2, x.data_ptr(), N, y.data_ptr(), sync=True)
