@@ -523,10 +523,15 @@ struct PairWalker {
 // Pass 2 is software pipelined two deep (ids for output j-2 and the 96-byte records for j-1 are in
 // flight while the multiplications of output j run): a thread's inputs are consecutive in the
 // level's list, but the table records behind the first level's ids are random 96-byte gathers.
-// Measured alternatives (B200, 2^18-point commits): no prefetch - same time; three CTAs per SM at 168
-// registers - slower (spills); two interleaved batches per thread for instruction-level
-// parallelism - slower (245 registers, no prefetch); a^(p-2) for the CTA's one inversion - the
-// single-lane dependent chain took 0.45 ms per launch, the binary Euclid inverse takes ~0.04 ms.
+// Measured alternatives (B200, 2^18-point commits; table in profiles/r01_msm_pair_levels.md): no
+// prefetch - same time; three CTAs per SM at 168 registers - slower (spills); two interleaved
+// batches per thread for instruction-level parallelism - slower (245 registers); two explicit
+// register sets instead of rotating one - slower; the denominator pass as its own kernel at twice
+// the occupancy - slower; L2 prefetch of the next group's records - slower; a^(p-2) for the CTA's one
+// inversion - the single-lane dependent chain took 0.45 ms per launch, the binary Euclid inverse
+// takes ~0.04 ms.  What remains (ncu): a strictly sequential product chain per thread at 2 warps
+// per scheduler (27 % issue-active against 31 % for the XYZZ kernel, which has two independent
+// products in flight) and long-scoreboard stalls in the denominator pass.
 template <class FQ, int FIRST, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_pairs(const uint32_t* entries, const void* src, const uint32_t* off_in,
                                                          const uint32_t* off_out, uint32_t nbuckets, uint32_t E, void* dst,
