@@ -526,12 +526,15 @@ def run_b200(args):
                        "l2": "inputs exceed L2 (resident base table %d MB)" % (n * 16 * 96 >> 20)},
             "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32,
                     "d2h_bytes_per_step": 144 + 15 * 192},
-            "roofline": {"kernel": "k_msm_accumulate", "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
+            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels, lists >= 6 M entries) + "
+                                   "k_msm_accumulate (XYZZ)",
+                         "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
                          "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": None,
                          "kernel_ms": acc, "kernel_share_of_step": acc / ms_per_step,
                          "peak_source": "measured live: independent mad.wide.u32 chains (apb_imad_peak)",
-                         "note": "algorithmic 48000 wide multiply-adds per point (SURVEY 8d); carry-chained "
-                                 "IMAD.WIDE.X issues at half the plain IMAD.WIDE rate, so 0.5 is this instruction mix's ceiling"},
+                         "note": "algorithmic 48000 wide multiply-adds per point (SURVEY 8d: XYZZ cost model); carry-chained "
+                                 "IMAD.WIDE.X issues at half the plain IMAD.WIDE rate, so 0.5 is the ceiling of a pure XYZZ "
+                                 "accumulation - the pair levels issue 6 products per addition instead of 10 and can exceed it"},
         }
         if rank == 0 and world == 1:
             v, dt = cpu_msm_baseline(min(log_n, 15), host_cores(), b"cpu")
