@@ -3,13 +3,14 @@
 #include <string.h>
 
 #include "common.cuh"
-#include "fp28.cuh"
 
 namespace apb {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-cudaStream_t g_stream = nullptr;
+cudaStream_t g_own_stream = nullptr;
+thread_local cudaStream_t t_user_stream = nullptr;
+int g_device = 0;
 bool g_inited = false;
 double g_last_ms = 0.0;
 std::recursive_mutex g_api_mutex;
@@ -105,82 +106,33 @@ __global__ void k_mul_bench(void* out, uint32_t iters) {
     if (s.v[0] == 0x12345 && s.v[1] == 77) store_fp<P>(out, 0, s);
 }
 
-// same for the reduced-radix product (fp28.cuh)
-template <class P28, int ILP>
-__global__ void k_mul_bench28(void* out, uint32_t iters) {
-    Fp28<P28> x[ILP], y = Fp28<P28>::one();
-    y.l[1] += 12345;
-#pragma unroll
-    for (int k = 0; k < ILP; k++) {
-        x[k] = Fp28<P28>::one();
-        x[k].l[0] += threadIdx.x + k;
-    }
-    for (uint32_t i = 0; i < iters; i++) {
-#pragma unroll
-        for (int k = 0; k < ILP; k++) x[k] = x[k] * y;
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < ILP; k++)
-        for (int i = 0; i < 14; i++) s ^= x[k].l[i];
-    if (s == 0x12345) ((uint32_t*)out)[0] = s;
-}
-
 }  // namespace apb
 
 using namespace apb;
 
 template <class P>
 static int run_mul_bench(int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
-    void* d_out = nullptr;
-    APB_CUDA_TRY(cudaMalloc(&d_out, 256));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    DevBuf out_buf;
+    APB_CUDA_TRY(out_buf.alloc(256));
+    void* d_out = out_buf.p;
+    EventPair ev;
     unsigned blocks = (unsigned)(g_num_sms * blocks_per_sm);
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
-        cudaEventRecord(e0, g_stream);
+        cudaEventRecord(ev.a, cur_stream());
         auto k1 = k_mul_bench<P, 1>;
         auto k2 = k_mul_bench<P, 2>;
         auto k4 = k_mul_bench<P, 4>;
         if (ilp == 1) APB_KLAUNCH(k1, blocks, threads, 0, d_out, iters);
         else if (ilp == 2) APB_KLAUNCH(k2, blocks, threads, 0, d_out, iters);
         else APB_KLAUNCH(k4, blocks, threads, 0, d_out, iters);
-        cudaEventRecord(e1, g_stream);
-        APB_CUDA_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventRecord(ev.b, cur_stream());
+        APB_CUDA_TRY(cudaEventSynchronize(ev.b));
+        const float ms = ev.ms();
         if (rep > 0 && ms < best) best = ms;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_out);
     int eff_ilp = ilp == 1 ? 1 : (ilp == 2 ? 2 : 4);
     *muls_per_s = (double)blocks * threads * iters * eff_ilp / (best * 1e-3);
-    return APB_OK;
-}
-
-static int run_mul_bench28(int threads, int blocks_per_sm, int ilp, uint32_t iters, double* muls_per_s) {
-    void* d_out = nullptr;
-    APB_CUDA_TRY(cudaMalloc(&d_out, 256));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    unsigned blocks = (unsigned)(g_num_sms * blocks_per_sm);
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
-        cudaEventRecord(e0, g_stream);
-        auto k1 = k_mul_bench28<Fq381_28, 1>;
-        auto k2 = k_mul_bench28<Fq381_28, 2>;
-        if (ilp == 1) APB_KLAUNCH(k1, blocks, threads, 0, d_out, iters);
-        else APB_KLAUNCH(k2, blocks, threads, 0, d_out, iters);
-        cudaEventRecord(e1, g_stream);
-        APB_CUDA_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (rep > 0 && ms < best) best = ms;
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_out);
-    *muls_per_s = (double)blocks * threads * iters * (ilp == 1 ? 1 : 2) / (best * 1e-3);
     return APB_OK;
 }
 
@@ -188,7 +140,6 @@ extern "C" int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp,
     APB_API_LOCK();
     APB_REQUIRE_INIT();
     if (!muls_per_s) return set_err(APB_ERR_INVALID_ARG, "apb_mul_bench: null out");
-    if (field == 4) return run_mul_bench28(threads, blocks_per_sm, ilp, iters, muls_per_s);
     switch (field) {
         case 0: return run_mul_bench<Fr381>(threads, blocks_per_sm, ilp, iters, muls_per_s);
         case 1: return run_mul_bench<Fq381>(threads, blocks_per_sm, ilp, iters, muls_per_s);
@@ -212,12 +163,22 @@ extern "C" int apb_init(int device) {
     cudaDeviceProp prop;
     APB_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     g_num_sms = prop.multiProcessorCount;
+    g_device = dev;              // every later entry point re-binds its calling thread to this device
 #else
     (void)device;
     g_num_sms = 1;
 #endif
-    APB_CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    APB_CUDA_TRY(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
     g_inited = true;
+    return APB_OK;
+}
+
+// Work of the calling host thread is enqueued on `stream` (a cudaStream_t of the library's device)
+// from now on; NULL returns to the library's own stream.  Device buffers produced on that stream
+// can then be handed to the _dev entry points without any host synchronisation, and sync = 0
+// calls return with their work merely enqueued there.
+extern "C" int apb_set_stream(void* stream) {
+    t_user_stream = (cudaStream_t)stream;
     return APB_OK;
 }
 
@@ -231,7 +192,7 @@ extern "C" const char* apb_version(void) {
 }
 extern "C" uint64_t apb_kernel_launches(void) { return g_launches.load(); }
 extern "C" double apb_last_device_ms(void) { return g_last_ms; }
-extern "C" void* apb_stream(void) { return (void*)g_stream; }
+extern "C" void* apb_stream(void) { return (void*)cur_stream(); }   // the stream this thread's calls use
 
 extern "C" int apb_dev_alloc(size_t bytes, void** d_ptr) {
     APB_API_LOCK();
@@ -249,21 +210,21 @@ extern "C" int apb_dev_free(void* d_ptr) {
 extern "C" int apb_dev_upload(void* d_dst, const void* h_src, size_t bytes) {
     APB_API_LOCK();
     APB_REQUIRE_INIT();
-    APB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 extern "C" int apb_dev_download(void* h_dst, const void* d_src, size_t bytes) {
     APB_API_LOCK();
     APB_REQUIRE_INIT();
-    APB_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 extern "C" int apb_dev_sync(void) {
     APB_API_LOCK();
     APB_REQUIRE_INIT();
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
@@ -274,12 +235,13 @@ extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t
     if (count == 0) return APB_OK;
     APB_REQUIRE_INIT();
     const size_t esz = (field == 0 || field == 2) ? 32 : 48;
-    void *da = nullptr, *db = nullptr, *dout = nullptr;
-    APB_CUDA_TRY(cudaMalloc(&da, count * esz));
-    APB_CUDA_TRY(cudaMalloc(&db, count * esz));
-    APB_CUDA_TRY(cudaMalloc(&dout, count * esz));
-    APB_CUDA_TRY(cudaMemcpyAsync(da, a, count * esz, cudaMemcpyHostToDevice, g_stream));
-    if (b) APB_CUDA_TRY(cudaMemcpyAsync(db, b, count * esz, cudaMemcpyHostToDevice, g_stream));
+    DevBuf ba, bb, bout;
+    APB_CUDA_TRY(ba.alloc(count * esz));
+    APB_CUDA_TRY(bb.alloc(count * esz));
+    APB_CUDA_TRY(bout.alloc(count * esz));
+    void *da = ba.p, *db = bb.p, *dout = bout.p;
+    APB_CUDA_TRY(cudaMemcpyAsync(da, a, count * esz, cudaMemcpyHostToDevice, cur_stream()));
+    if (b) APB_CUDA_TRY(cudaMemcpyAsync(db, b, count * esz, cudaMemcpyHostToDevice, cur_stream()));
     unsigned blocks = (unsigned)((count + 127) / 128);
     switch (field) {
         case 0: APB_KLAUNCH(k_field_op<Fr381>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
@@ -288,39 +250,35 @@ extern "C" int apb_field_op(int field, int op, const uint64_t* a, const uint64_t
         default: APB_KLAUNCH(k_field_op<Fq377>, blocks, 128, 0, op, (const void*)da, (const void*)db, dout, (uint64_t)count); break;
     }
     APB_CHECK_LAUNCH();
-    APB_CUDA_TRY(cudaMemcpyAsync(out, dout, count * esz, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
-    cudaFree(da); cudaFree(db); cudaFree(dout);
+    APB_CUDA_TRY(cudaMemcpyAsync(out, dout, count * esz, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
 extern "C" int apb_imad_peak(double* wide_per_s, double* imad32_per_s) {
     APB_API_LOCK();
     APB_REQUIRE_INIT();
-    uint32_t* d_out = nullptr;
-    APB_CUDA_TRY(cudaMalloc((void**)&d_out, 64));
+    DevBuf out_buf;
+    APB_CUDA_TRY(out_buf.alloc(64));
+    uint32_t* d_out = out_buf.as<uint32_t>();
     const uint32_t iters = 4096;
     const unsigned blocks = (unsigned)g_num_sms * 8, threads = 256;
     double res[2] = {0, 0};
     for (int wide = 0; wide < 2; wide++) {
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        EventPair ev;
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
-            cudaEventRecord(e0, g_stream);
+            cudaEventRecord(ev.a, cur_stream());
             if (wide) APB_KLAUNCH(k_imad_bench<1>, blocks, threads, 0, d_out, iters, 12345u + rep);
             else APB_KLAUNCH(k_imad_bench<0>, blocks, threads, 0, d_out, iters, 12345u + rep);
-            cudaEventRecord(e1, g_stream);
-            APB_CUDA_TRY(cudaEventSynchronize(e1));
-            float ms = 0;
-            cudaEventElapsedTime(&ms, e0, e1);
+            cudaEventRecord(ev.b, cur_stream());
+            APB_CUDA_TRY(cudaEventSynchronize(ev.b));
+            const float ms = ev.ms();
             if (rep > 0 && ms < best) best = ms;
         }
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         double ops = (double)blocks * threads * iters * 32.0;
         res[wide] = best > 0 ? ops / (best * 1e-3) : 0;
     }
-    cudaFree(d_out);
     if (wide_per_s) *wide_per_s = res[1];
     if (imad32_per_s) *imad32_per_s = res[0];
     return APB_OK;

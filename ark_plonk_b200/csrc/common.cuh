@@ -14,10 +14,46 @@ namespace apb {
 
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
-extern cudaStream_t g_stream;
+extern cudaStream_t g_own_stream;                    // created by apb_init; used when the caller set none
+extern thread_local cudaStream_t t_user_stream;     // apb_set_stream: the calling host thread's stream
 extern bool g_inited;
+extern int g_device;                                // the device apb_init bound the library to
 extern double g_last_ms;
-extern std::recursive_mutex g_api_mutex;   // the library has one stream and shared workspaces: entry points serialise
+// Entry points that take a handle (commitment key, domain) serialise on THAT handle's mutex and use
+// only its workspaces, so two handles driven from two host threads / streams run concurrently.
+// Handle-less entry points (polynomial utilities: one shared workspace) serialise on g_api_mutex.
+extern std::recursive_mutex g_api_mutex;
+
+// the stream every launch / copy of the current entry point is enqueued on
+inline cudaStream_t cur_stream() { return t_user_stream ? t_user_stream : g_own_stream; }
+// CUDA's current device is per host thread: entry points may be called from any thread
+inline void bind_device() {
+#ifndef APB_EMU
+    if (g_inited) cudaSetDevice(g_device);
+#endif
+}
+struct ApiGuard {
+    std::unique_lock<std::recursive_mutex> lk;
+    explicit ApiGuard(std::recursive_mutex& m) : lk(m) { bind_device(); }
+};
+// temporary device buffers / events of one entry point: released on every return path
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    float ms() const { float v = 0; cudaEventElapsedTime(&v, a, b); return v; }
+};
 
 int set_err(int code, const char* fmt, ...);
 
@@ -32,10 +68,11 @@ int set_err(int code, const char* fmt, ...);
 #define APB_KLAUNCH(kernel, grid, block, smem, ...)                                         \
     do {                                                                                    \
         apb::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
-        APB_LAUNCH(kernel, grid, block, smem, apb::g_stream, __VA_ARGS__);                  \
+        APB_LAUNCH(kernel, grid, block, smem, apb::cur_stream(), __VA_ARGS__);                  \
     } while (0)
 
-#define APB_API_LOCK() std::lock_guard<std::recursive_mutex> apb_api_lock_(apb::g_api_mutex)
+#define APB_API_LOCK() apb::ApiGuard apb_api_lock_(apb::g_api_mutex)
+#define APB_HANDLE_LOCK(h) apb::ApiGuard apb_handle_lock_((h)->mu)
 
 #define APB_CHECK_LAUNCH() APB_CUDA_TRY(cudaGetLastError())
 
@@ -92,12 +129,10 @@ APB_D void store_fp(void* base, size_t idx, const Fp<P>& a) {
 struct Curve381 {
     typedef Fr381 FR;
     typedef Fq381 FQ;
-    typedef Fq381_28 FQ28;
 };
 struct Curve377 {
     typedef Fr377 FR;
     typedef Fq377 FQ;
-    typedef Fq377_28 FQ28;
 };
 
 }  // namespace apb

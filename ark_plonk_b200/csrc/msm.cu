@@ -30,7 +30,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "fp28.cuh"
 #include "host_ec.hpp"
 #include "scan_u32.cuh"
 
@@ -235,102 +234,6 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* en
         __syncwarp();
         if (more) { e_cur = e_nxt; px = nx; py = ny; }
     }
-}
-
-// Same walk with the accumulator in reduced radix (fp28.cuh): the resident table holds x*2^392
-// mod p, the mixed addition runs on carry-free IMAD.WIDE columns, and a flushed bucket is mapped
-// back to the library-wide 2^384 Montgomery form.
-template <class P28>
-__device__ __noinline__ void flush28(const XYZZ28<P28>& acc, void* dst, uint64_t idx) {
-    typedef typename P28::Base FQ;
-    XYZZ<FQ> o;
-    if (acc.inf) {
-        o = XYZZ<FQ>::identity();
-    } else {
-        o.x = acc.x.to_mont384();
-        o.y = acc.y.to_mont384();
-        o.zz = acc.zz.to_mont384();
-        o.zzz = acc.zzz.to_mont384();
-    }
-    store_xyzz<FQ>(dst, idx, o);
-}
-
-template <class P28, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_msm_accumulate28(const uint32_t* entries, const uint32_t* offsets, uint32_t nbuckets,
-                                                                const void* bases, uint32_t E, void* bucket_sums, void* partials,
-                                                                int32_t* part_bucket) {
-    typedef typename P28::Base FQ;
-    typedef Fp<FQ> W;             // packed 12-word records as loaded
-    typedef Fp28<P28> F;
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t M = offsets[nbuckets];
-    part_bucket[2 * t] = -1;
-    part_bucket[2 * t + 1] = -1;
-    uint64_t pos = t * E;
-    if (pos >= M) return;
-    const uint64_t end = pos + E < M ? pos + E : M;
-    uint32_t lo = 0, hi = nbuckets;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= pos) lo = mid; else hi = mid;
-    }
-    uint32_t b = lo;
-    while (offsets[b + 1] <= pos) b++;
-    uint32_t e_cur = entries[pos];
-    W px, py;
-    load_affine<FQ>(bases, e_cur & 0x7fffffffu, px, py);
-    uint64_t bstart = offsets[b], bend = offsets[b + 1], run_start = pos;
-    XYZZ28<P28> acc;
-    acc.set_identity();
-    while (pos < end) {
-        uint32_t e_nxt = 0;
-        W nx, ny;
-        const bool more = pos + 1 < end;
-        if (more) {
-            e_nxt = entries[pos + 1];
-            load_affine<FQ>(bases, e_nxt & 0x7fffffffu, nx, ny);
-        }
-        if (!(px.is_zero() && py.is_zero())) {               // skip the point at infinity
-            F ax = F::from_words(px.v), ay = F::from_words(py.v);
-            if (e_cur >> 31) ay = ay.neg_canonical();
-            acc.add_affine(ax, ay);
-        }
-        pos++;
-        if (pos == bend || pos == end) {                     // run finished: flush
-            const bool head = run_start == bstart, tail = pos == bend;
-            if (head && tail) {
-                flush28<P28>(acc, bucket_sums, b);
-            } else if (head) {
-                flush28<P28>(acc, partials, 2 * t + 1);
-                part_bucket[2 * t + 1] = (int32_t)b;
-            } else {
-                flush28<P28>(acc, partials, 2 * t);
-                part_bucket[2 * t] = (int32_t)b;
-            }
-            if (pos < end) {
-                b++;
-                while (offsets[b + 1] <= pos) b++;
-                bstart = offsets[b];
-                bend = offsets[b + 1];
-                run_start = pos;
-                acc.set_identity();
-            }
-        }
-        __syncwarp();
-        if (more) { e_cur = e_nxt; px = nx; py = ny; }
-    }
-}
-
-// in place: table entries x*2^384 -> x*2^392 (mod p)
-template <class P28>
-__global__ void k_table_to392(void* bases, uint64_t count) {
-    typedef typename P28::Base FQ;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Fp<FQ> c;
-#pragma unroll
-    for (int k = 0; k < 12; k++) c.v[k] = P28::to392(k);
-    store_fp<FQ>(bases, i, load_fp<FQ>(bases, i) * c);
 }
 
 // stitch buckets that straddle chunk borders: the chunk holding the head piece sums the rest
@@ -738,12 +641,11 @@ static const uint32_t CK_MAGIC = 0x434b3031;
 
 struct apb_ck_s {
     uint32_t magic;
+    std::recursive_mutex mu;       // entry points on one key serialise here (APB_HANDLE_LOCK)
     int curve;
     size_t n;
     uint32_t F, step;
-    void* bases;                   // F * n affine points (x*2^392 domain when radix == 28)
-    void* bases_orig;              // the n points as uploaded (download / diagnostics)
-    int radix;                     // 28: reduced-radix accumulate (default); 32: carry-chain accumulate
+    void* bases;                   // F * n affine points: copy f holds 2^(step*f) * P_i
     // workspace (grown on demand)
     void* d_scalars; size_t scalars_cap;
     uint32_t *counts, *offsets, *cursors; size_t buckets_cap;
@@ -779,8 +681,7 @@ static int grow(T** p, size_t* cap, size_t need_bytes) {
 }
 
 static int ck_alloc(int curve, size_t n, apb_ck_s** out) {
-    apb_ck_s* ck = new apb_ck_s();
-    memset(ck, 0, sizeof(*ck));
+    apb_ck_s* ck = new apb_ck_s();           // value-initialised: all members zero
     ck->magic = CK_MAGIC;
     ck->curve = curve;
     ck->n = n;
@@ -798,26 +699,22 @@ static int ck_alloc(int curve, size_t n, apb_ck_s** out) {
     *out = ck;
     return APB_OK;
 }
+struct CkOwner {                 // unique ownership of a key under construction
+    apb_ck_s* ck;
+    explicit CkOwner(apb_ck_s* c) : ck(c) {}
+    CkOwner(const CkOwner&) = delete;
+    CkOwner& operator=(const CkOwner&) = delete;
+    ~CkOwner() { if (ck) apb_ck_free(ck); }
+    apb_ck_s* release() { apb_ck_s* c = ck; ck = nullptr; return c; }
+};
+
 static int ck_precompute(apb_ck_s* ck) {
     if (!ck->n) return APB_OK;
     unsigned blocks = (unsigned)((ck->n + 127) / 128);
     if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_ck_precompute<Fq381>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
     else APB_KLAUNCH(k_ck_precompute<Fq377>, blocks, 128, 0, ck->bases, (uint64_t)ck->n, ck->F, ck->step);
-    // 32: carry-chained 32-bit limbs (default, 30.9 G Fq-mul/s measured); 28: reduced-radix experiment
-    // (carry-free IMAD.WIDE columns) - measured SLOWER on sm_100a (20.6 G mul/s: the plain IMAD.WIDE
-    // with distinct register operands and the extra ALU work do not dual-issue as hoped), kept
-    // selectable for the record: profiles/r01_mul_bench_radix28.json
-    ck->radix = 32;
-    if (const char* e = getenv("APB_MSM_RADIX")) ck->radix = atoi(e) == 28 ? 28 : 32;
-    if (ck->radix == 28) {
-        APB_CUDA_TRY(cudaMalloc(&ck->bases_orig, ck->n * 96));
-        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases_orig, ck->bases, ck->n * 96, cudaMemcpyDeviceToDevice, g_stream));
-        const uint64_t count = (uint64_t)ck->n * ck->F * 2;
-        if (ck->curve == APB_CURVE_BLS12_381) APB_KLAUNCH(k_table_to392<Fq381_28>, (unsigned)((count + 127) / 128), 128, 0, ck->bases, count);
-        else APB_KLAUNCH(k_table_to392<Fq377_28>, (unsigned)((count + 127) / 128), 128, 0, ck->bases, count);
-    }
     APB_CHECK_LAUNCH();
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
@@ -827,22 +724,25 @@ static int ck_precompute(apb_ck_s* ck) {
 extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const uint64_t* tau, size_t n, apb_ck_t* out) {
     APB_API_LOCK();
     if (!out || !generator_xy || !tau) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: null argument");
+    *out = nullptr;
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_from_tau: bad curve %d", curve);
     APB_REQUIRE_INIT();
     apb_ck_s* ck = nullptr;
     int rc = ck_alloc(curve, n, &ck);
     if (rc != APB_OK) return rc;
+    CkOwner owner(ck);                          // frees the half-built key on any early return
     if (n) {
         host::Field f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fr381>() : host::Field::make<Fr377>();
         uint64_t h_pow2[64 * 4], cur[4];
         memcpy(cur, tau, 32);
         for (int k = 0; k < 64; k++) { memcpy(h_pow2 + 4 * k, cur, 32); f.sqr(cur, cur); }
-        void *d_pow2 = nullptr, *d_powers = nullptr, *d_gen = nullptr;
-        APB_CUDA_TRY(cudaMalloc(&d_pow2, sizeof(h_pow2)));
-        APB_CUDA_TRY(cudaMalloc(&d_powers, n * 32));
-        APB_CUDA_TRY(cudaMalloc(&d_gen, 96));
-        APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2, sizeof(h_pow2), cudaMemcpyHostToDevice, g_stream));
-        APB_CUDA_TRY(cudaMemcpyAsync(d_gen, generator_xy, 96, cudaMemcpyHostToDevice, g_stream));
+        DevBuf b_pow2, b_powers, b_gen;
+        APB_CUDA_TRY(b_pow2.alloc(sizeof(h_pow2)));
+        APB_CUDA_TRY(b_powers.alloc(n * 32));
+        APB_CUDA_TRY(b_gen.alloc(96));
+        void *d_pow2 = b_pow2.p, *d_powers = b_powers.p, *d_gen = b_gen.p;
+        APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2, sizeof(h_pow2), cudaMemcpyHostToDevice, cur_stream()));
+        APB_CUDA_TRY(cudaMemcpyAsync(d_gen, generator_xy, 96, cudaMemcpyHostToDevice, cur_stream()));
         unsigned blocks = (unsigned)((n + 127) / 128);
         if (curve == APB_CURVE_BLS12_381) {
             APB_KLAUNCH(k_tau_powers<Fr381>, blocks, 128, 0, d_powers, (uint64_t)n, (const void*)d_pow2);
@@ -852,22 +752,21 @@ extern "C" int apb_ck_from_tau(int curve, const uint64_t* generator_xy, const ui
             APB_KLAUNCH(k_srs_powers<Curve377>, blocks, 128, 0, ck->bases, (const void*)d_powers, (uint64_t)n, (const void*)d_gen);
         }
         APB_CHECK_LAUNCH();
-        APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
-        cudaFree(d_pow2); cudaFree(d_powers); cudaFree(d_gen);
-        if ((rc = ck_precompute(ck)) != APB_OK) { apb_ck_free(ck); return rc; }
+        APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
+        if ((rc = ck_precompute(ck)) != APB_OK) return rc;
     }
-    *out = ck;
+    *out = owner.release();
     return APB_OK;
 }
 
 // copies `count` resident powers starting at `first` to host memory (12 u64 each)
 extern "C" int apb_ck_download(apb_ck_t ck, size_t first, size_t count, uint64_t* out_xy) {
-    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC || !out_xy) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_download: bad handle");
+    APB_HANDLE_LOCK(ck);
     if (first + count > ck->n) return set_err(APB_ERR_INVALID_ARG, "apb_ck_download: range exceeds key size");
-    const char* src = (const char*)(ck->bases_orig ? ck->bases_orig : ck->bases);
-    APB_CUDA_TRY(cudaMemcpyAsync(out_xy, src + first * 96, count * 96, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    const char* src = (const char*)ck->bases;
+    APB_CUDA_TRY(cudaMemcpyAsync(out_xy, src + first * 96, count * 96, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
@@ -876,19 +775,20 @@ extern "C" int apb_ck_upload(int curve, const uint64_t* xy, size_t n, apb_ck_t* 
     if (!out || (!xy && n)) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: null argument");
     if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_ck_upload: bad curve %d", curve);
     APB_REQUIRE_INIT();
+    *out = nullptr;
     apb_ck_s* ck = nullptr;
     int rc = ck_alloc(curve, n, &ck);
     if (rc != APB_OK) return rc;
+    CkOwner owner(ck);
     if (n) {
-        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases, xy, n * 96, cudaMemcpyHostToDevice, g_stream));
-        if ((rc = ck_precompute(ck)) != APB_OK) { apb_ck_free(ck); return rc; }
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->bases, xy, n * 96, cudaMemcpyHostToDevice, cur_stream()));
+        if ((rc = ck_precompute(ck)) != APB_OK) return rc;
     }
-    *out = ck;
+    *out = owner.release();
     return APB_OK;
 }
 
 extern "C" int apb_ck_size(apb_ck_t ck, size_t* n) {
-    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_ck_size: bad handle");
     *n = ck->n;
     return APB_OK;
@@ -896,8 +796,13 @@ extern "C" int apb_ck_size(apb_ck_t ck, size_t* n) {
 
 extern "C" void apb_ck_free(apb_ck_t ck) {
     if (!ck || ck->magic != CK_MAGIC) return;
+    {   // wait for a call that is still using this key's workspaces, then retire the handle
+        APB_HANDLE_LOCK(ck);
+        cudaStreamSynchronize(cur_stream());
+        ck->magic = 0;
+    }
     // offsets / cursors / stage_b are interior pointers of counts / stage_a
-    cudaFree(ck->bases); cudaFree(ck->bases_orig); cudaFree(ck->d_scalars); cudaFree(ck->counts);
+    cudaFree(ck->bases); cudaFree(ck->d_scalars); cudaFree(ck->counts);
     cudaFree(ck->scan_tmp);
     cudaFree(ck->entries); cudaFree(ck->bucket_sums); cudaFree(ck->partials);
     cudaFree(ck->part_bucket); cudaFree(ck->stage_a); cudaFree(ck->jobs);
@@ -905,7 +810,6 @@ extern "C" void apb_ck_free(apb_ck_t ck) {
     if (ck->h_out) cudaFreeHost(ck->h_out);
     delete ck->h_jobs_a;
     delete ck->h_jobs_b;
-    ck->magic = 0;
     delete ck;
 }
 
@@ -947,6 +851,13 @@ static bool build_jobs(apb_ck_s* ck, uint32_t c, uint32_t windows, uint32_t& a_b
     return true;
 }
 
+// bucket entries (scalars x digit positions) one pass can sort: positions are uint32
+static uint64_t max_entries_per_pass() {
+    uint64_t lim = ((uint64_t)1 << 32) - 1;
+    if (const char* e = getenv("APB_MSM_MAX_ENTRIES")) lim = (uint64_t)atoll(e);      // tests force the split path at small sizes
+    return lim;
+}
+
 template <class CV>
 static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int mont, uint64_t* out_xyz) {
     typedef typename CV::FR FR;
@@ -967,6 +878,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     const uint32_t windows = B.k * g.G;
     const uint32_t nbuckets = windows * g.hb;
     const uint64_t Mmax = (uint64_t)total * g.W;
+    // list positions, bucket offsets and cursors are 32-bit: the batch entry points split larger requests
+    if (Mmax + nbuckets >= max_entries_per_pass()) return set_err(APB_ERR_INVALID_ARG, "apb_msm: %llu bucket entries exceed the 32-bit list of one pass", (unsigned long long)Mmax);
     if ((uint64_t)ck->F * ck->n >= ((uint64_t)1 << 31)) return set_err(APB_ERR_INVALID_ARG, "apb_msm: key too large for 31-bit point ids");
 
     // batched-affine pair levels in front of the XYZZ accumulate: worth it when buckets are long
@@ -983,7 +896,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if (const char* e = getenv("APB_MSM_AFFINE_MAX_BYTES")) max_bytes = (uint64_t)atoll(e);
         if (max_levels > 6) max_levels = 6;
         const uint64_t need = (Mmax / 2 + nbuckets) * (96 + 48 + 8) + (Mmax / 4 + 2 * (uint64_t)nbuckets) * 96;
-        bool want = ck->radix == 32 && Mmax >= min_entries && Mmax < ((uint64_t)1 << 31);
+        bool want = Mmax >= min_entries && Mmax < ((uint64_t)1 << 31);
         if (want && need > max_bytes) {
             // too large for the budget in one piece: run the stage over equal BUCKET RANGES one after the other
             // (the list is sorted by bucket, so a range of buckets is a contiguous piece of it)
@@ -1014,9 +927,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         occupancy_known = 1;
 #ifndef APB_EMU
         int nb = 0;
-        if (ck->radix == 28) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate28<typename CV::FQ28, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
-        } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2, 0>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2, 0>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_pairs<FQ, 1, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
 #endif
     }
@@ -1078,8 +989,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     const size_t jobs_cap_before = ck->jobs_cap;
     if ((rc = grow(&ck->jobs, &ck->jobs_cap, (njobs_a + njobs_b) * sizeof(TreeJob))) != APB_OK) return rc;
     if (jobs_new || jobs_cap_before != ck->jobs_cap) {
-        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs, ck->h_jobs_a->data(), njobs_a * sizeof(TreeJob), cudaMemcpyHostToDevice, g_stream));
-        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs + njobs_a, ck->h_jobs_b->data(), njobs_b * sizeof(TreeJob), cudaMemcpyHostToDevice, g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs, ck->h_jobs_a->data(), njobs_a * sizeof(TreeJob), cudaMemcpyHostToDevice, cur_stream()));
+        APB_CUDA_TRY(cudaMemcpyAsync(ck->jobs + njobs_a, ck->h_jobs_b->data(), njobs_b * sizeof(TreeJob), cudaMemcpyHostToDevice, cur_stream()));
     }
     const size_t out_bytes = (size_t)windows * per_b * 192;
     if (ck->h_out_cap < out_bytes) {
@@ -1089,11 +1000,16 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         ck->h_out_cap = out_bytes;
     }
 
-    cudaEvent_t ev[6];
-    if (g_profile) { for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], g_stream); }
+    struct PhaseEvents {               // per-phase timers while profiling; destroyed on every return path
+        cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool on = false;
+        ~PhaseEvents() { if (on) for (int i = 0; i < 6; i++) cudaEventDestroy(e[i]); }
+    } pev;
+    cudaEvent_t* ev = pev.e;
+    if (g_profile) { pev.on = true; for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], cur_stream()); }
     // 1. histogram  2. scan  3. scatter
-    APB_CUDA_TRY(cudaMemsetAsync(ck->counts, 0, (size_t)(nbuckets + 1) * 4 * 3, g_stream));
-    APB_CUDA_TRY(cudaMemsetAsync(ck->bucket_sums, 0, (size_t)nbuckets * 192, g_stream));
+    APB_CUDA_TRY(cudaMemsetAsync(ck->counts, 0, (size_t)(nbuckets + 1) * 4 * 3, cur_stream()));
+    APB_CUDA_TRY(cudaMemsetAsync(ck->bucket_sums, 0, (size_t)nbuckets * 192, cur_stream()));
     dim3 dgrid((unsigned)((max_len + 255) / 256), B.k);
     auto k_hist = k_msm_digits<FR, 0>;
     auto k_scatter = k_msm_digits<FR, 1>;
@@ -1103,10 +1019,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if (rc2 != APB_OK) return rc2;
     }
     APB_KLAUNCH(k_scatter, dgrid, 256, 0, d_scalars, B, g, mont, ck->counts, (const uint32_t*)ck->offsets, ck->cursors, ck->entries);
-    if (g_profile) cudaEventRecord(ev[1], g_stream);
+    if (g_profile) cudaEventRecord(ev[1], cur_stream());
     // 4. pair levels (batched-affine)  5. accumulate  6. stitch - over the whole bucket range, or slice by slice
-    typedef typename CV::FQ28 FQ28;
-    auto k_acc28 = k_msm_accumulate28<FQ28, 2>;
     auto k_acc2 = k_msm_accumulate<FQ, 2, 0>;
     auto k_acc_lvl = k_msm_accumulate<FQ, 2, 1>;
     auto k_pairs_first = k_msm_pairs<FQ, 1, 2>;
@@ -1115,8 +1029,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     std::vector<uint32_t> bound(slices + 1);
     if (slices > 1) {
         for (uint32_t sl = 0; sl <= slices; sl++)
-            APB_CUDA_TRY(cudaMemcpyAsync(&bound[sl], ck->offsets + (size_t)sl * nbS, 4, cudaMemcpyDeviceToHost, g_stream));
-        APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+            APB_CUDA_TRY(cudaMemcpyAsync(&bound[sl], ck->offsets + (size_t)sl * nbS, 4, cudaMemcpyDeviceToHost, cur_stream()));
+        APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
         for (uint32_t sl = 0; sl < slices; sl++) unbalanced = unbalanced || (uint64_t)(bound[sl + 1] - bound[sl]) > Mslice;
     }
     if (unbalanced) {
@@ -1171,26 +1085,23 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if (levels)
             APB_KLAUNCH(k_acc_lvl, (unsigned)blocks_s, 128, 0, (const uint32_t*)nullptr, acc_offsets, nbS,
                         (const void*)ck->lvl_pts[(levels - 1) & 1], Es, sums, ck->partials, ck->part_bucket);
-        else if (ck->radix == 28)
-            APB_KLAUNCH(k_acc28, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
-                        (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
         else
             APB_KLAUNCH(k_acc2, (unsigned)acc_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
                         (const void*)ck->bases, E, ck->bucket_sums, ck->partials, ck->part_bucket);
         APB_KLAUNCH(k_msm_stitch<FQ>, (unsigned)blocks_s, 128, 0, acc_offsets, Es, (uint64_t)(blocks_s * 128), sums,
                     (const void*)ck->partials, (const int32_t*)ck->part_bucket);
     }
-    if (g_profile) cudaEventRecord(ev[2], g_stream);
-    if (g_profile) cudaEventRecord(ev[3], g_stream);
+    if (g_profile) cudaEventRecord(ev[2], cur_stream());
+    if (g_profile) cudaEventRecord(ev[3], cur_stream());
     // 6. bucket reduction trees
     APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)((njobs_a + 3) / 4), 128, 0, (const void*)ck->bucket_sums, ck->stage_a, (const TreeJob*)ck->jobs,
                 (uint32_t)njobs_a);
     APB_KLAUNCH(k_msm_tree<FQ>, (unsigned)((njobs_b + 3) / 4), 128, 0, (const void*)ck->stage_a, ck->stage_b,
                 (const TreeJob*)(ck->jobs + njobs_a), (uint32_t)njobs_b);
     APB_CHECK_LAUNCH();
-    if (g_profile) cudaEventRecord(ev[4], g_stream);
-    APB_CUDA_TRY(cudaMemcpyAsync(ck->h_out, ck->stage_b, out_bytes, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    if (g_profile) cudaEventRecord(ev[4], cur_stream());
+    APB_CUDA_TRY(cudaMemcpyAsync(ck->h_out, ck->stage_b, out_bytes, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     if (g_profile) {
         for (int i = 0; i < 4; i++) {
             float ms = 0;
@@ -1205,7 +1116,6 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
             g_madds_model += (double)Mmax * 3000.0;
             g_madds_issued += issued + m * 3000.0;
         }
-        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
 
     // 7. host epilogue: Horner over weight bits, fold windows, then normalise all k results with ONE
@@ -1257,30 +1167,45 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
 }
 
 static int msm_dispatch(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int mont, uint64_t* out) {
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, g_stream);
+    EventPair ev;
+    cudaEventRecord(ev.a, cur_stream());
     int rc = ck->curve == APB_CURVE_BLS12_381 ? run_msm<Curve381>(ck, B, d_scalars, mont, out)
                                                : run_msm<Curve377>(ck, B, d_scalars, mont, out);
-    cudaEventRecord(e1, g_stream);
-    cudaEventSynchronize(e1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    g_last_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaEventRecord(ev.b, cur_stream());
+    cudaEventSynchronize(ev.b);
+    g_last_ms = ev.ms();
     return rc;
+}
+
+// how many of the polynomials lens[0..avail) go into one pass: at most MAX_BATCH, and the bucket-entry
+// list (scalars x digit positions) of the pass must stay below the 32-bit position limit
+static uint32_t batch_take(const apb_ck_s* ck, const size_t* lens, size_t avail) {
+    const uint32_t bits = ck->curve == APB_CURVE_BLS12_381 ? (uint32_t)Fr381::BITS : (uint32_t)Fr377::BITS;
+    const uint64_t limit = max_entries_per_pass();
+    size_t max_len = 0, total = 0;
+    uint32_t take = 0;
+    while (take < (uint32_t)MAX_BATCH && take < avail) {
+        const size_t ml = std::max(max_len, lens[take]), tot = total + lens[take];
+        MsmGeom g;
+        choose_geom(ck, ml, g, bits);
+        if (take > 0 && (uint64_t)tot * g.W + (uint64_t)(take + 1) * g.G * g.hb >= limit) break;
+        max_len = ml;
+        total = tot;
+        take++;
+    }
+    return take;
 }
 
 extern "C" int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scalars, const size_t* base_offsets,
                              const size_t* lens, int mont, uint64_t* out_xyz) {
-    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm: bad key handle");
+    APB_HANDLE_LOCK(ck);
     if (k == 0) return APB_OK;
     if (!scalars || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm: null argument");
-    for (size_t done = 0; done < k; done += MAX_BATCH) {
+    for (size_t done = 0; done < k;) {
         MsmBatch B;
         memset(&B, 0, sizeof(B));
-        B.k = (uint32_t)std::min<size_t>(MAX_BATCH, k - done);
+        B.k = batch_take(ck, lens + done, k - done);
         size_t total = 0;
         for (uint32_t j = 0; j < B.k; j++) {
             size_t off = base_offsets ? base_offsets[done + j] : 0, len = lens[done + j];
@@ -1295,23 +1220,23 @@ extern "C" int apb_msm_batch(apb_ck_t ck, size_t k, const uint64_t* const* scala
         if (rc != APB_OK) return rc;
         for (uint32_t j = 0; j < B.k; j++)
             if (B.len[j])
-                APB_CUDA_TRY(cudaMemcpyAsync((char*)ck->d_scalars + B.scal_off[j] * 32, scalars[done + j], B.len[j] * 32, cudaMemcpyHostToDevice, g_stream));
+                APB_CUDA_TRY(cudaMemcpyAsync((char*)ck->d_scalars + B.scal_off[j] * 32, scalars[done + j], B.len[j] * 32, cudaMemcpyHostToDevice, cur_stream()));
         rc = msm_dispatch(ck, B, ck->d_scalars, mont, out_xyz + 18 * done);
         if (rc != APB_OK) return rc;
+        done += B.k;
     }
     return APB_OK;
 }
 
 extern "C" int apb_msm(apb_ck_t ck, size_t base_offset, const uint64_t* scalars, size_t n, int mont, uint64_t out_xyz[18]) {
-    APB_API_LOCK();
     const uint64_t* sp[1] = {scalars};
     size_t off[1] = {base_offset}, len[1] = {n};
     return apb_msm_batch(ck, 1, sp, off, len, mont, out_xyz);
 }
 
 extern "C" int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalars, size_t n, int mont, uint64_t out_xyz[18]) {
-    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_dev: bad key handle");
+    APB_HANDLE_LOCK(ck);
     if (!out_xyz || (n && !d_scalars)) return set_err(APB_ERR_INVALID_ARG, "apb_msm_dev: null argument");
     if (base_offset + n > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm_dev: %zu scalars at base offset %zu exceed the %zu resident powers", n, base_offset, ck->n);
     MsmBatch B;
@@ -1325,14 +1250,14 @@ extern "C" int apb_msm_dev(apb_ck_t ck, size_t base_offset, const void* d_scalar
 // d_scalars: one device buffer; scal_offs in elements
 extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t* scal_offs, const size_t* base_offsets,
                                  const size_t* lens, int mont, uint64_t* out_xyz) {
-    APB_API_LOCK();
     if (!ck || ck->magic != CK_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_msm_batch_dev: bad key handle");
+    APB_HANDLE_LOCK(ck);
     if (k == 0) return APB_OK;
     if (!d_scalars || !scal_offs || !lens || !out_xyz) return set_err(APB_ERR_INVALID_ARG, "apb_msm_batch_dev: null argument");
-    for (size_t done = 0; done < k; done += MAX_BATCH) {
+    for (size_t done = 0; done < k;) {
         MsmBatch B;
         memset(&B, 0, sizeof(B));
-        B.k = (uint32_t)std::min<size_t>(MAX_BATCH, k - done);
+        B.k = batch_take(ck, lens + done, k - done);
         for (uint32_t j = 0; j < B.k; j++) {
             size_t off = base_offsets ? base_offsets[done + j] : 0, len = lens[done + j];
             if (off + len > ck->n) return set_err(APB_ERR_TOO_MANY_COEFFS, "apb_msm: %zu scalars at base offset %zu exceed the %zu resident powers", len, off, ck->n);
@@ -1342,6 +1267,7 @@ extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, c
         }
         int rc = msm_dispatch(ck, B, d_scalars, mont, out_xyz + 18 * done);
         if (rc != APB_OK) return rc;
+        done += B.k;
     }
     return APB_OK;
 }

@@ -166,6 +166,7 @@ using namespace apb;
 
 struct apb_domain_s {
     uint32_t magic;
+    std::recursive_mutex mu;              // entry points on one domain serialise here (APB_HANDLE_LOCK)
     int curve;
     uint32_t log_n;
     size_t n;
@@ -199,25 +200,25 @@ static int build_tables(apb_domain_s* d) {
     f.inv(ninv, nval);
     for (int i = 0; i < 4; i++) { d->size_inv[2 * i] = (uint32_t)ninv[i]; d->size_inv[2 * i + 1] = (uint32_t)(ninv[i] >> 32); }
 
-    uint64_t* h_pow2 = (uint64_t*)malloc(4 * 64 * 8 * 4);      // 4 bases x 64 powers
+    std::vector<uint64_t> h_pow2(4 * 64 * 4);                  // 4 bases x 64 powers
     const uint64_t* bases[4] = {w, winv, g, ginv};
     for (int b = 0; b < 4; b++) {
         uint64_t cur[4];
         f.set(cur, bases[b]);
         for (int k = 0; k < 64; k++) {
-            memcpy(h_pow2 + (b * 64 + k) * 4, cur, 32);
+            memcpy(h_pow2.data() + (b * 64 + k) * 4, cur, 32);
             f.sqr(cur, cur);
         }
     }
-    void* d_pow2 = nullptr;
-    void* d_scale = nullptr;
-    APB_CUDA_TRY(cudaMalloc(&d_pow2, 4 * 64 * 32));
-    APB_CUDA_TRY(cudaMalloc(&d_scale, 64));
-    APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2, 4 * 64 * 32, cudaMemcpyHostToDevice, g_stream));
+    DevBuf b_pow2, b_scale;
+    APB_CUDA_TRY(b_pow2.alloc(4 * 64 * 32));
+    APB_CUDA_TRY(b_scale.alloc(64));
+    void *d_pow2 = b_pow2.p, *d_scale = b_scale.p;
+    APB_CUDA_TRY(cudaMemcpyAsync(d_pow2, h_pow2.data(), 4 * 64 * 32, cudaMemcpyHostToDevice, cur_stream()));
     uint64_t scales[8];
     memcpy(scales, f.one, 32);
     memcpy(scales + 4, ninv, 32);
-    APB_CUDA_TRY(cudaMemcpyAsync(d_scale, scales, 64, cudaMemcpyHostToDevice, g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(d_scale, scales, 64, cudaMemcpyHostToDevice, cur_stream()));
 
     const size_t half = d->n > 1 ? d->n / 2 : 1;
     const size_t nhi = (d->n >> COSET_LO_BITS) + 1, nlo = (size_t)1 << COSET_LO_BITS;
@@ -238,10 +239,7 @@ static int build_tables(apb_domain_s* d) {
     // 1/N folded into the high table of the inverse coset scale
     APB_KLAUNCH(k_pow_table<FR>, blocks(nhi), 128, 0, d->ichi, (uint64_t)nhi, (const void*)(p2 + 3 * 64 * 32), (uint32_t)COSET_LO_BITS, (const void*)(sc + 32));
     APB_CHECK_LAUNCH();
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
-    cudaFree(d_pow2);
-    cudaFree(d_scale);
-    free(h_pow2);
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
@@ -266,8 +264,8 @@ extern "C" int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out) {
     uint32_t adicity = curve == APB_CURVE_BLS12_381 ? (uint32_t)Fr381::TWO_ADICITY : (uint32_t)Fr377::TWO_ADICITY;
     if (log_n > adicity || log_n > 30) return set_err(APB_ERR_DOMAIN_TOO_LARGE, "apb_domain_new: log_n %u exceeds supported size", log_n);
     APB_REQUIRE_INIT();
-    apb_domain_s* d = new apb_domain_s();
-    memset(d, 0, sizeof(*d));
+    *out = nullptr;
+    apb_domain_s* d = new apb_domain_s();      // value-initialised: all members zero
     d->magic = DOMAIN_MAGIC;
     d->curve = curve;
     d->log_n = log_n;
@@ -280,7 +278,6 @@ extern "C" int apb_domain_new(int curve, uint32_t log_n, apb_domain_t* out) {
 }
 
 extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
-    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC || !n) return set_err(APB_ERR_BAD_HANDLE, "apb_domain_size: bad handle");
     *n = d->n;
     return APB_OK;
@@ -288,7 +285,6 @@ extern "C" int apb_domain_size(apb_domain_t d, size_t* n) {
 
 // internal: lets the polynomial kernels reach the resident root table w^i, i < N/2
 extern "C" int apb_domain_info(apb_domain_t d, int* curve, uint32_t* log_n, const void** tw) {
-    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "bad domain handle");
     *curve = d->curve;
     *log_n = d->log_n;
@@ -298,10 +294,14 @@ extern "C" int apb_domain_info(apb_domain_t d, int* curve, uint32_t* log_n, cons
 
 extern "C" void apb_domain_free(apb_domain_t d) {
     if (!d || d->magic != DOMAIN_MAGIC) return;
+    {   // wait for a call that is still using this domain's scratch, then retire the handle
+        APB_HANDLE_LOCK(d);
+        cudaStreamSynchronize(cur_stream());
+        d->magic = 0;
+    }
     cudaFree(d->tw); cudaFree(d->itw); cudaFree(d->clo); cudaFree(d->chi);
     cudaFree(d->iclo); cudaFree(d->ichi); cudaFree(d->scratch);
     cudaFree(d->io_in); cudaFree(d->io_out);
-    d->magic = 0;
     delete d;
 }
 
@@ -394,28 +394,28 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
 
 extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, size_t in_stride, void* d_out,
                                  size_t out_stride, size_t batch, int sync) {
-    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
+    APB_HANDLE_LOCK(d);
     if (kind < 0 || kind > 3) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: bad kind %d", kind);
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
     if (batch == 0) return APB_OK;
     if (!d_out || (!d_in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (g_profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, g_stream); }
+    struct Ev2 { cudaEvent_t *a, *b; ~Ev2() { if (*a) cudaEventDestroy(*a); if (*b) cudaEventDestroy(*b); } } pev{&pe0, &pe1};
+    if (g_profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cur_stream()); }
     int rc = d->curve == APB_CURVE_BLS12_381
                  ? run_ntt<Fr381>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch)
                  : run_ntt<Fr377>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch);
     if (g_profile) {
-        cudaEventRecord(pe1, g_stream);
+        cudaEventRecord(pe1, cur_stream());
         cudaEventSynchronize(pe1);
         float ms = 0;
         cudaEventElapsedTime(&ms, pe0, pe1);
         g_ntt_ms_total += ms;
         g_ntt_count += batch;
-        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
     }
     if (rc != APB_OK) return rc;
-    if (sync) APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    if (sync) APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return APB_OK;
 }
 
@@ -426,14 +426,13 @@ extern "C" void apb_ntt_totals(double* ms, unsigned long long* transforms, int r
 }
 
 extern "C" int apb_ntt_dev(apb_domain_t d, int kind, const void* d_in, size_t in_len, void* d_out, int sync) {
-    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
     return apb_ntt_batch_dev(d, kind, d_in, in_len, d->n, d_out, d->n, 1, sync);
 }
 
 extern "C" int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_len, uint64_t* out) {
-    APB_API_LOCK();
     if (!d || d->magic != DOMAIN_MAGIC) return set_err(APB_ERR_BAD_HANDLE, "apb_ntt: bad domain handle");
+    APB_HANDLE_LOCK(d);
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
     if (!out || (!in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
     if (!d->io_in) {
@@ -441,20 +440,19 @@ extern "C" int apb_ntt(apb_domain_t d, int kind, const uint64_t* in, size_t in_l
         APB_CUDA_TRY(cudaMalloc(&d->io_out, d->n * 32));
     }
     void *d_in = d->io_in, *d_out = d->io_out;
-    if (in_len) APB_CUDA_TRY(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, g_stream));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, g_stream);
+    if (in_len) APB_CUDA_TRY(cudaMemcpyAsync(d_in, in, in_len * 32, cudaMemcpyHostToDevice, cur_stream()));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
+    cudaEventRecord(e0, cur_stream());
     int rc = apb_ntt_dev(d, kind, d_in, in_len, d_out, 0);
-    cudaEventRecord(e1, g_stream);
+    cudaEventRecord(e1, cur_stream());
     if (rc == APB_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, d_out, d->n * 32, cudaMemcpyDeviceToHost, g_stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        cudaError_t e = cudaMemcpyAsync(out, d_out, d->n * 32, cudaMemcpyDeviceToHost, cur_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cur_stream());
         if (e != cudaSuccess) rc = set_err(APB_ERR_CUDA, "apb_ntt: %s", cudaGetErrorString(e));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         g_last_ms = ms;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }

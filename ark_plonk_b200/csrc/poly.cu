@@ -626,8 +626,8 @@ static int grand_product(size_t n, void* d_z) {
     if ((rc = fr_scan<FR, 0>(num, pn, n, 0, tot)) != APB_OK) return rc;
     if ((rc = fr_scan<FR, 0>(den, sd, n, 1, (char*)tot + 32)) != APB_OK) return rc;
     uint64_t h_tot[4], h_inv[4];
-    APB_CUDA_TRY(cudaMemcpyAsync(h_tot, (char*)tot + 32, 32, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(h_tot, (char*)tot + 32, 32, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     host::Field f = host::Field::make<FR>();
     if (f.is_zero(h_tot)) return set_err(APB_ERR_INVALID_ARG, "grand product: zero denominator (inverse().unwrap() panics in the reference)");
     f.inv(h_inv, h_tot);
@@ -721,9 +721,9 @@ extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d
     uint32_t *owner = w, *first = owner + cap, *count = first + cap, *half = count + cap, *odd = half + (n + 1),
              *oddpre = odd + (n + 1), *esz = oddpre + (n + 1), *osz = esz + (n + 1), *eoff = osz + (n + 1),
              *ooff = eoff + (n + 1), *blk = ooff + (n + 1), *misc = blk + nb + 1;
-    APB_CUDA_TRY(cudaMemsetAsync(owner, 0xff, (size_t)2 * cap * 4, g_stream));       // owner, first = 0xffffffff
-    APB_CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)cap * 4, g_stream));
-    APB_CUDA_TRY(cudaMemsetAsync(misc, 0, 64, g_stream));
+    APB_CUDA_TRY(cudaMemsetAsync(owner, 0xff, (size_t)2 * cap * 4, cur_stream()));       // owner, first = 0xffffffff
+    APB_CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)cap * 4, cur_stream()));
+    APB_CUDA_TRY(cudaMemsetAsync(misc, 0, 64, cur_stream()));
     APB_KLAUNCH(k_cs_hash, nblk(n, 128), 128, 0, d_t, d_f, (uint64_t)n, mask, owner, first, count, 0, misc);
     APB_KLAUNCH(k_cs_hash, nblk(n, 128), 128, 0, d_t, d_f, (uint64_t)n, mask, owner, first, count, 1, misc);
     APB_KLAUNCH(k_cs_bucket_sizes, nblk(n, 128), 128, 0, d_t, (uint64_t)n, mask, (const uint32_t*)owner, (const uint32_t*)first,
@@ -733,15 +733,15 @@ extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d
     if ((rc = u32_scan(esz, eoff, n, blk, misc + 2)) != APB_OK) return rc;
     if ((rc = u32_scan(osz, ooff, n, blk, misc + 3)) != APB_OK) return rc;
     uint32_t h_misc[4];
-    APB_CUDA_TRY(cudaMemcpyAsync(h_misc, misc, 16, cudaMemcpyDeviceToHost, g_stream));
-    APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(h_misc, misc, 16, cudaMemcpyDeviceToHost, cur_stream()));
+    APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     if (h_misc[0]) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_combine_split: ElementNotIndexed (an element of f is not in t)");
     const uint32_t n_even = h_misc[2], n_odd = h_misc[3];
     if (n_even != n || n_odd != n)
         return set_err(APB_ERR_INVALID_ARG, "apb_plonk_combine_split: halves of %u / %u elements (expected %zu each)", n_even, n_odd, n);
     // sentinel offsets[n] = total so the fill kernel's search terminates
-    APB_CUDA_TRY(cudaMemcpyAsync(eoff + n, misc + 2, 4, cudaMemcpyDeviceToDevice, g_stream));
-    APB_CUDA_TRY(cudaMemcpyAsync(ooff + n, misc + 3, 4, cudaMemcpyDeviceToDevice, g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(eoff + n, misc + 2, 4, cudaMemcpyDeviceToDevice, cur_stream()));
+    APB_CUDA_TRY(cudaMemcpyAsync(ooff + n, misc + 3, 4, cudaMemcpyDeviceToDevice, cur_stream()));
     APB_KLAUNCH(k_cs_fill, nblk(n, 128), 128, 0, d_t, (const uint32_t*)eoff, (uint64_t)n, d_h1, (uint64_t)n);
     APB_KLAUNCH(k_cs_fill, nblk(n, 128), 128, 0, d_t, (const uint32_t*)ooff, (uint64_t)n, d_h2, (uint64_t)n);
     APB_CHECK_LAUNCH();
@@ -834,7 +834,7 @@ static int poly_eval_impl(size_t k, const void* const* d_polys, const size_t* le
         }
         A.E = E1;
         A.in_stride_blocks = nb1;
-        APB_CUDA_TRY(cudaMemcpyAsync(dargs, &A, sizeof(EvalArgs), cudaMemcpyHostToDevice, g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(dargs, &A, sizeof(EvalArgs), cudaMemcpyHostToDevice, cur_stream()));
         APB_KLAUNCH(k_eval_level<FR>, dim3((unsigned)nb1, kk), EVAL_T, 0, (const EvalArgs*)dargs, lvl1);
         // level 2: nb1 partials per polynomial in the variable x^(2048); one block each
         if (nb1 > 1) {
@@ -849,12 +849,12 @@ static int poly_eval_impl(size_t k, const void* const* d_polys, const size_t* le
             B.E = E2;
             B.in_stride_blocks = 1;
             EvalArgs* dB = (EvalArgs*)dargs + 1;
-            APB_CUDA_TRY(cudaMemcpyAsync(dB, &B, sizeof(EvalArgs), cudaMemcpyHostToDevice, g_stream));
+            APB_CUDA_TRY(cudaMemcpyAsync(dB, &B, sizeof(EvalArgs), cudaMemcpyHostToDevice, cur_stream()));
             APB_KLAUNCH(k_eval_level<FR>, dim3(1, kk), EVAL_T, 0, (const EvalArgs*)dB, lvl2);
         }
         APB_CHECK_LAUNCH();
-        APB_CUDA_TRY(cudaMemcpyAsync(out_vals + 4 * done, nb1 > 1 ? lvl2 : lvl1, (size_t)kk * 32, cudaMemcpyDeviceToHost, g_stream));
-        APB_CUDA_TRY(cudaStreamSynchronize(g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(out_vals + 4 * done, nb1 > 1 ? lvl2 : lvl1, (size_t)kk * 32, cudaMemcpyDeviceToHost, cur_stream()));
+        APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     }
     return APB_OK;
 }
@@ -876,7 +876,7 @@ static int divide_impl(const void* d_p, size_t len, const uint64_t* z, void* d_o
     host::Field f = host::Field::make<FR>();
     if (len <= 1) return APB_OK;
     if (f.is_zero(z)) {      // p / X: shift
-        APB_CUDA_TRY(cudaMemcpyAsync(d_out, (const char*)d_p + 32, (len - 1) * 32, cudaMemcpyDeviceToDevice, g_stream));
+        APB_CUDA_TRY(cudaMemcpyAsync(d_out, (const char*)d_p + 32, (len - 1) * 32, cudaMemcpyDeviceToDevice, cur_stream()));
         return APB_OK;
     }
     uint64_t zinv[4];
@@ -897,7 +897,7 @@ static int divide_impl(const void* d_p, size_t len, const uint64_t* z, void* d_o
     if ((rc = ws_get(0, len * 32, &a)) != APB_OK) return rc;
     if ((rc = ws_get(1, len * 32, &b)) != APB_OK) return rc;
     tot = (char*)pw + 2 * 64 * 32;
-    APB_CUDA_TRY(cudaMemcpyAsync(pw, h_pow2, sizeof(h_pow2), cudaMemcpyHostToDevice, g_stream));
+    APB_CUDA_TRY(cudaMemcpyAsync(pw, h_pow2, sizeof(h_pow2), cudaMemcpyHostToDevice, cur_stream()));
     // a[j] = z^j ; b[j] = p_j z^j ; a <- exclusive suffix sums of b: a[i] = sum_{j>i} p_j z^j
     APB_KLAUNCH(k_pow_seq<FR>, nblk(len, 128), 128, 0, a, (uint64_t)len, (const void*)pw, (uint64_t)0);
     APB_KLAUNCH(k_mul_pointwise<FR>, nblk(len, 128), 128, 0, d_p, (const void*)a, b, (uint64_t)len);

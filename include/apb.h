@@ -13,9 +13,12 @@
  *   - Every function returns an `apb_status`; nothing unwinds across the boundary;
  *     `apb_last_error()` gives a thread-local message.
  *   - Handles own device memory (bases, twiddles) which stays resident in HBM until freed.
- *   - `_dev` variants take device pointers and enqueue on the handle's stream without a host
- *     synchronisation; the plain variants block until results are in host memory (the
- *     semantics of the reference's synchronous Rust calls).
+ *   - `_dev` variants take device pointers and enqueue on the CALLING THREAD's stream - the one
+ *     given to `apb_set_stream` (a cudaStream_t), else the library's own - without a host
+ *     synchronisation; buffers produced on that stream need no external sync.  The plain variants
+ *     block until results are in host memory (the semantics of the reference's synchronous Rust
+ *     calls).  Entry points on one handle serialise on that handle; different handles (their
+ *     workspaces are private) can be driven concurrently from different threads / streams.
  *   - One process drives one GPU (`apb_init(device)`); multi-GPU sharding is done by the
  *     host layer with one process per GPU.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
@@ -55,7 +58,11 @@ typedef struct apb_ck_s* apb_ck_t;          /* resident CommitterKey powers (Son
 typedef struct apb_domain_s* apb_domain_t;  /* resident Radix2EvaluationDomain (twiddles) */
 
 /* ---- library ---------------------------------------------------------------------------- */
-int apb_init(int device);                   /* idempotent; binds this process to one GPU */
+int apb_init(int device);                   /* idempotent; binds this process to one GPU (every entry point re-binds its calling thread) */
+/* stream (cudaStream_t, as void*) that the calling host thread's later calls enqueue on; NULL = the
+ * library's own stream.  SURVEY 8(b): "apb_*_dev(...): same, device pointers + cudaStream_t, no host sync". */
+int apb_set_stream(void* cuda_stream);
+void* apb_stream(void);                     /* the stream this thread's calls currently use */
 const char* apb_last_error(void);
 const char* apb_version(void);
 

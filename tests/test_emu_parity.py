@@ -42,9 +42,6 @@ def test_msm_duplicate_points_and_cancellation(emu_lib):
     with pc.env(APB_MSM_C=8, APB_MSM_CHUNK=3):
         pc.check_msm_duplicates(emu_lib, 0)
         pc.check_msm_duplicates(emu_lib, 1)
-    with pc.env(APB_MSM_C=8, APB_MSM_CHUNK=3, APB_MSM_RADIX=28):      # reduced-radix (28-bit limb) variant of the accumulate kernel
-        pc.check_msm_duplicates(emu_lib, 0)
-        pc.check_msm_tau(emu_lib, 0, 40)
 
 
 def test_msm_bls12_377_and_batch(emu_lib):

@@ -57,9 +57,6 @@ def test_msm_progression_large(gpu_lib, curve, n, k):
 def test_msm_duplicate_points_and_cancellation(gpu_lib):
     pc.check_msm_duplicates(gpu_lib, 0)
     pc.check_msm_duplicates(gpu_lib, 1)
-    with pc.env(APB_MSM_RADIX=28):          # reduced-radix (28-bit limb) variant of the accumulate kernel
-        pc.check_msm_duplicates(gpu_lib, 0)
-        pc.check_msm_tau(gpu_lib, 0, 3000)
 
 
 @pytest.mark.parametrize("curve", [0, 1])

@@ -17,8 +17,6 @@ with pc.env(APB_MSM_C=8, APB_MSM_CHUNK=5, APB_NTT_MAX_LOG_TILE=3, APB_NTT_LOG_CO
     pc.check_msm_progression(lib, 0, 48, k=3)
     poly_cases.check_lincomb_eval_divide(lib, 0, 300); poly_cases.check_combine_split(lib, 0)
     poly_cases.check_grand_products(lib, 0, 5)
-with pc.env(APB_MSM_C=8, APB_MSM_RADIX=28):
-    pc.check_msm_tau(lib, 0, 20)
 with pc.env(APB_MSM_C=8, APB_NTT_MAX_LOG_TILE=4):
     prover_cases.prove_case(lib, prover_cases.golden_case(0, 5))
 print("ASAN clean")
