@@ -71,6 +71,7 @@ class Lib:
         c.apb_dev_upload.argtypes = [vp, vp, sz]
         c.apb_dev_download.argtypes = [vp, vp, sz]
         c.apb_stream.restype = vp
+        c.apb_set_stream.argtypes = [vp]
         c.apb_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
         c.apb_kernel_launches.restype = C.c_uint64
         c.apb_imad_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -98,6 +99,9 @@ class Lib:
         c.apb_msm_phase_ms.restype = None
         c.apb_msm_work.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), ci]
         c.apb_msm_work.restype = None
+        c.apb_msm_call_ms.argtypes = [C.POINTER(C.c_double), ci]
+        c.apb_msm_call_ms.restype = None
+        c.apb_msm_last_plan.restype = None
 
     # ------------------------------------------------------------------
     def check(self, rc: int):
@@ -106,6 +110,11 @@ class Lib:
 
     def init(self, device: int = -1):
         self.check(self.c.apb_init(device))
+
+    def set_stream(self, cuda_stream: int | None):
+        """enqueue this thread's later calls on `cuda_stream` (a cudaStream_t as int, e.g.
+        torch.cuda.current_stream().cuda_stream); None = the library's own stream"""
+        self.check(self.c.apb_set_stream(cuda_stream))
 
     def version(self) -> str:
         return self.c.apb_version().decode()
@@ -124,6 +133,17 @@ class Lib:
         a, b = C.c_double(0), C.c_double(0)
         self.c.apb_msm_work(C.byref(a), C.byref(b), 1 if reset else 0)
         return a.value, b.value
+
+    def msm_call_ms(self, reset: bool = False) -> float:
+        """device ms of whole MSM calls since the last reset (while profiling)"""
+        v = C.c_double(0)
+        self.c.apb_msm_call_ms(C.byref(v), 1 if reset else 0)
+        return v.value
+
+    def msm_last_plan(self):
+        arr = (C.c_uint32 * 4)()
+        self.c.apb_msm_last_plan(arr)
+        return dict(zip(("digit_bits", "pair_levels", "slices", "unbalanced"), list(arr)))
 
     def msm_phase_ms(self):
         arr = (C.c_double * 4)()

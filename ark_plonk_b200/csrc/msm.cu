@@ -38,10 +38,12 @@ namespace apb {
 int g_num_sms = 1;
 int g_profile = 0;
 double g_acc_ms_total = 0.0;            // accumulated k_msm_accumulate time while profiling
+double g_msm_call_ms_total = 0.0;       // whole MSM calls (sort + accumulation + reduction + copy + host epilogue) while profiling
 unsigned long long g_points_total = 0;  // scalars processed while profiling
 double g_madds_model = 0.0;             // while profiling: wide multiply-adds by the XYZZ cost model (entries x 10 x 300)
 double g_madds_issued = 0.0;            // ... and as issued: 6 x 300 per batched-affine pair addition, 10 x 300 per XYZZ one
 double g_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sort, accumulate, stitch, trees, copy+host epilogue
+uint32_t g_last_plan[4] = {0, 0, 0, 0};            // of the last pass: digit bits, pair levels, bucket-range slices, fell back (unbalanced)
 
 static const int MAX_BATCH = 16;
 static const int MAX_COPIES = 16;
@@ -1033,6 +1035,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
         for (uint32_t sl = 0; sl < slices; sl++) unbalanced = unbalanced || (uint64_t)(bound[sl + 1] - bound[sl]) > Mslice;
     }
+    g_last_plan[0] = g.c; g_last_plan[1] = levels; g_last_plan[2] = slices; g_last_plan[3] = unbalanced ? 1u : 0u;
     if (unbalanced) {
         if (getenv("APB_MSM_DEBUG")) fprintf(stderr, "apb_msm: unbalanced slices, plain accumulate\n");
         APB_KLAUNCH(k_acc2, (unsigned)fb_blocks, 128, 0, (const uint32_t*)ck->entries, (const uint32_t*)ck->offsets, nbuckets,
@@ -1174,6 +1177,7 @@ static int msm_dispatch(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, 
     cudaEventRecord(ev.b, cur_stream());
     cudaEventSynchronize(ev.b);
     g_last_ms = ev.ms();
+    if (g_profile) g_msm_call_ms_total += g_last_ms;
     return rc;
 }
 
@@ -1273,6 +1277,12 @@ extern "C" int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, c
 }
 
 extern "C" void apb_set_profiling(int on) { g_profile = on; }
+// diagnostics (tests assert which path a call took): {digit bits, pair levels, bucket-range slices, unbalanced fallback}
+extern "C" void apb_msm_last_plan(uint32_t out[4]) { for (int i = 0; i < 4; i++) out[i] = g_last_plan[i]; }
+extern "C" void apb_msm_call_ms(double* whole_calls_ms, int reset) {
+    if (whole_calls_ms) *whole_calls_ms = g_msm_call_ms_total;
+    if (reset) g_msm_call_ms_total = 0.0;
+}
 extern "C" void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset) {
     if (accumulate_ms) *accumulate_ms = g_acc_ms_total;
     if (points) *points = g_points_total;

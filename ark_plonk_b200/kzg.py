@@ -29,14 +29,16 @@ class CommitterKey:
         self._h = h
 
     @classmethod
-    def from_tau(cls, curve: int, tau: int, n: int, lib: Lib | None = None) -> "CommitterKey":
-        """`PC::setup` + `trim` with a known tau: [tau^i]G, i < n, generated on the device."""
+    def from_tau(cls, curve: int, tau: int, n: int, lib: Lib | None = None, generator=None) -> "CommitterKey":
+        """`PC::setup` + `trim` with a known tau: [tau^i]G, i < n, generated on the device.
+        `generator`: affine (x, y) ints to use instead of the standard G1 generator (KZG10::setup draws a random
+        one; a rank of a point-split key passes tau^(first index) G to get its slice of the powers)."""
         from .synth import G1_GENERATOR
         self = cls.__new__(cls)
         self.lib = lib or get_lib()
         self.curve = curve
         self.n = n
-        gen = enc.g1_affine_to_mont(curve, [G1_GENERATOR[curve]])
+        gen = enc.g1_affine_to_mont(curve, [generator if generator is not None else G1_GENERATOR[curve]])
         t = enc.fr_to_mont(curve, [tau])
         h = C.c_void_p()
         self.lib.check(self.lib.c.apb_ck_from_tau(curve, gen.ctypes.data, t.ctypes.data, n, C.byref(h)))

@@ -5,8 +5,9 @@
   scalars, and the per-rank partial sums (one normalised point, 144 bytes) are exchanged with a
   single all-gather; every rank folds the G partials on the host (G-1 group additions).
   NCCL has no elliptic-curve reduction, so reduction = gather + local adds.
-* A single NTT does not shard (replicas only); independent polynomials / proofs are distributed
-  across ranks by the caller (`bench.py --workload prove --gpus N`).
+* `DistributedCommitter`: one proof over N GPUs, SPMD - every rank runs the prover, the MSM work of
+  every commit batch is split evenly, only 144-byte partial sums are exchanged.
+* A single NTT does not shard (replicas only).
 """
 from __future__ import annotations
 
@@ -60,110 +61,81 @@ def sharded_msm(ck: ShardedCommitterKey, scalars: np.ndarray, montgomery: bool =
     return acc
 
 
-class DistributedCommitter:
-    """Per-polynomial task split of `PC::commit` over the ranks of a process group (SURVEY.md 8e,
-    "batched prove").  Every rank holds the full commitment key resident; rank 0 runs the prover and,
-    for each batch of k polynomials, broadcasts the coefficient vectors (k x n x 32 B over
-    NVLink), every rank multiplies the polynomials j with j % world == rank, and the normalised
-    results (144 B each) are combined with one all-reduce.  Workers sit in `serve()`.
-    The transcript, NTTs and pointwise kernels stay on rank 0 (they depend on each commitment).
-    """
-    OP_STOP, OP_COMMIT = 0, 1
+def split_pieces(lens, world: int):
+    """Equal-work split of a batch of polynomials over `world` ranks: the coefficient ranges of the k
+    polynomials are laid end to end and cut into `world` equal contiguous parts, so every rank multiplies
+    the same number of points whatever k is (k = 3 over 2 ranks, k = 2 over 8, ...).  Returns the ordered
+    piece list [(poly j, lo, hi, owner rank)]; at most k + world - 1 pieces."""
+    lens = [int(x) for x in lens]
+    total = sum(lens)
+    pieces = []
+    if total == 0:
+        return pieces
+    cuts = [total * r // world for r in range(world + 1)]
+    start = 0
+    for j, ln in enumerate(lens):
+        end = start + ln
+        for r in range(world):
+            lo, hi = max(start, cuts[r]), min(end, cuts[r + 1])
+            if hi > lo:
+                pieces.append((j, lo - start, hi - start, r))
+        start = end
+    return pieces
 
-    def __init__(self, curve: int, ck: "kzg.CommitterKey", n_max: int, k_max: int = 8, group=None, device: str = "cuda",
+
+class DistributedCommitter:
+    """SPMD split of `PC::commit` over the ranks of a process group (SURVEY.md 8e, "batched prove").
+
+    Every rank runs the WHOLE prover on the same witness (same transcript, same challenges) and holds the
+    full commitment key resident, so no polynomial ever crosses NVLink: for each batch of k polynomials a
+    rank multiplies only its pieces (`split_pieces`: equal point counts per rank, cut across polynomial
+    borders), writes the normalised partial sums (144 B each) into its slots of a small result vector,
+    and ONE all-reduce of that vector (<= (k + world - 1) x 144 B) gives every rank all partial sums; each
+    rank folds the pieces of a polynomial on the host (a handful of group additions) and continues with
+    identical commitments.  Round 1 broadcast the coefficient vectors from rank 0 instead (64 MiB per
+    8-polynomial batch) and kept NTTs / pointwise work on rank 0 only.
+    """
+
+    def __init__(self, curve: int, ck: "kzg.CommitterKey", n_max: int = 0, k_max: int = 16, group=None, device: str = "cuda",
                  lib: Lib | None = None):
-        self.curve, self.ck, self.n, self.k_max, self.group, self.device = curve, ck, n_max, k_max, group, device
+        self.curve, self.ck, self.k_max, self.group, self.device = curve, ck, k_max, group, device
         self.lib = lib or get_lib()
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.header = torch.zeros(2 + k_max, dtype=torch.int64, device=device)
-        self.stage = torch.zeros(k_max * n_max * 4, dtype=torch.int64, device=device)
-        self.results = torch.zeros(k_max * max(self.world, 1) * 18, dtype=torch.int64, device=device)
-        self._stream = None
-        if device == "cuda":
-            self._stream = torch.cuda.ExternalStream(self.lib.c.apb_stream())
-
-    def _ctx(self):
-        import contextlib
-        return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
-
-    def _tasks(self, k: int, lens):
-        """work of this rank for a batch of k polynomials: [(poly j, lo, hi, result slot)], slices per poly S.
-        k >= world: whole polynomials round-robin; k < world: every polynomial is cut into world // k
-        contiguous coefficient ranges (point split inside the polynomial split)"""
-        W, r = self.world, self.rank
-        if k >= W:
-            return [(j, 0, int(lens[j]), j) for j in range(k) if j % W == r], 1
-        S = W // k
-        if r >= k * S:
-            return [], S
-        j, sidx = r % k, r // k
-        per = (int(lens[j]) + S - 1) // S
-        lo = min(sidx * per, int(lens[j]))
-        hi = min(lo + per, int(lens[j]))
-        return ([(j, lo, hi, j * S + sidx)] if hi > lo else []), S
-
-    def _local_msms(self, k: int, lens) -> int:
-        """MSMs of this rank's share of the staged polynomials -> self.results slots (others zero)"""
-        import ctypes as C
-        tasks, S = self._tasks(k, lens)
-        self.results.zero_()
-        if tasks:
-            m = len(tasks)
-            so = (C.c_size_t * m)(*[j * self.n + lo for j, lo, _, _ in tasks])
-            bo = (C.c_size_t * m)(*[lo for _, lo, _, _ in tasks])
-            ln = (C.c_size_t * m)(*[hi - lo for _, lo, hi, _ in tasks])
-            out = np.zeros((m, 18), dtype=np.uint64)
-            self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, m, self.stage.data_ptr(), so, bo, ln, 1, out.ctypes.data))
-            host = torch.from_numpy(out.view(np.int64))
-            for i, (_, _, _, slot) in enumerate(tasks):
-                self.results[slot * 18:(slot + 1) * 18].copy_(host[i])
-        return S
+        self.results = torch.zeros((k_max + max(self.world, 1)) * 18, dtype=torch.int64, device=device)
+        self.batches = 0
 
     def commit(self, arena, offs, lens) -> np.ndarray:
-        """rank 0: commitments of the k polynomials at arena offsets `offs` -> (k, 18) uint64"""
+        """called by EVERY rank with its own copy of the k polynomials at arena element offsets `offs`:
+        commitments of all k polynomials -> (k, 18) uint64, identical on every rank"""
+        import ctypes as C
         k = len(offs)
         out = np.zeros((k, 18), dtype=np.uint64)
         for base in range(0, k, self.k_max):
             kk = min(self.k_max, k - base)
-            with self._ctx():
-                hdr = [self.OP_COMMIT, kk] + [int(x) for x in lens[base:base + kk]] + [0] * (self.k_max - kk)
-                self.header.copy_(torch.tensor(hdr, dtype=torch.int64))
-                for j in range(kk):
-                    self.stage[j * self.n * 4:(j * self.n + int(lens[base + j])) * 4].copy_(arena.view(offs[base + j], int(lens[base + j])))
-                dist.broadcast(self.header, src=0, group=self.group)
-                dist.broadcast(self.stage[: kk * self.n * 4], src=0, group=self.group)
-                if self._stream is not None:
-                    self._stream.synchronize()
-                S = self._local_msms(kk, lens[base:base + kk])
-                dist.all_reduce(self.results, group=self.group)
-                parts = self.results[: kk * S * 18].cpu().numpy().view(np.uint64).reshape(kk, S, 18)
-                for j in range(kk):
-                    acc = parts[j, 0]
-                    for sidx in range(1, S):               # fold the point slices of polynomial j (host, 144-byte points)
-                        acc = self.lib.g1_add(self.curve, acc, parts[j, sidx])
-                    out[base + j] = acc
+            pieces = split_pieces(lens[base:base + kk], self.world)
+            mine = [(i, p) for i, p in enumerate(pieces) if p[3] == self.rank]
+            res = self.results[: max(len(pieces), 1) * 18]
+            res.zero_()
+            if mine:
+                m = len(mine)
+                so = (C.c_size_t * m)(*[int(offs[base + j]) + lo for _, (j, lo, _, _) in mine])
+                bo = (C.c_size_t * m)(*[lo for _, (_, lo, _, _) in mine])
+                ln = (C.c_size_t * m)(*[hi - lo for _, (_, lo, hi, _) in mine])
+                part = np.zeros((m, 18), dtype=np.uint64)
+                self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, m, arena.base, so, bo, ln, 1, part.ctypes.data))
+                host = torch.from_numpy(part.view(np.int64))
+                for row, (slot, _) in enumerate(mine):
+                    res[slot * 18:(slot + 1) * 18].copy_(host[row])
+            if self.world > 1:
+                dist.all_reduce(res, group=self.group)          # slots are disjoint: the sum is a gather
+            parts = res.cpu().numpy().view(np.uint64).reshape(-1, 18)
+            done = set()
+            for slot, (j, _, _, _) in enumerate(pieces):
+                if j in done:
+                    out[base + j] = self.lib.g1_add(self.curve, out[base + j], parts[slot])
+                else:
+                    out[base + j] = parts[slot]
+                    done.add(j)
+            self.batches += 1
         return out
-
-    def serve(self) -> int:
-        """worker ranks: answer commit requests until rank 0 calls `shutdown`; returns #batches served"""
-        served = 0
-        while True:
-            with self._ctx():
-                dist.broadcast(self.header, src=0, group=self.group)
-                hdr = self.header.cpu().tolist()
-                if hdr[0] == self.OP_STOP:
-                    return served
-                kk = hdr[1]
-                dist.broadcast(self.stage[: kk * self.n * 4], src=0, group=self.group)
-                if self._stream is not None:
-                    self._stream.synchronize()
-                self._local_msms(kk, hdr[2:2 + kk])
-                dist.all_reduce(self.results, group=self.group)
-            served += 1
-
-    def shutdown(self):
-        if self.world > 1 and self.rank == 0:
-            with self._ctx():
-                self.header.zero_()
-                dist.broadcast(self.header, src=0, group=self.group)

@@ -217,7 +217,7 @@ class Prover:
         sig_names = ["left_sigma", "right_sigma", "out_sigma", "fourth_sigma"]
         # residents: (8 selectors + 4 sigmas) polys + 4 tables + q_lookup evals + scratch ; 14 vectors of 4n
         # + the per-proof working set of `prove` (24 n-vectors, 11 4n-vectors, openings)
-        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 32) * n + (len(names) + 4 + 2 + 12) * 4 * n,
+        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 36) * n + (len(names) + 4 + 2 + 12) * 4 * n,
                       torch_device=self.arena_device)
         pk = ProverKey(curve=curve, n=n, arena=arena, dom=dom, dom4=dom4, custom=custom,
                        public_inputs={int(k): int(v) % p for k, v in circ.public_inputs.items() if int(v) % p})
@@ -306,29 +306,40 @@ class Prover:
             arena.upload(off, np.ascontiguousarray(wires_mont).reshape(4 * n, 4))
 
     def prove(self, pk: ProverKey, wires_mont, transcript_label: bytes = b"ark", faithful: bool = True,
-              trace: dict | None = None, wires_resident: int | None = None):
+              trace: dict | None = None, wires_resident: int | None = None, public_inputs: dict | None = None):
         """wires_mont: (4, n, 4) uint64 Montgomery wire values (w_l, w_r, w_o, w_4), padded to n.
         `faithful`: also issue the 14 commitments of prover.rs:579,606 whose results the reference
-        discards (SonicKZG10::open ignores them) so that the MSM count matches the reference's 29."""
+        discards (SonicKZG10::open ignores them) so that the MSM count matches the reference's 29.
+        `public_inputs`: {row: value} of THIS proof (the reference reads them from the composer per
+        proof, prover.rs:182,392; the key holds structure only); default = the values of the circuit the
+        key was compiled from."""
         curve, n, p, lib = self.curve, pk.n, self.p, self.lib
         N4 = 4 * n
         dom, dom4 = pk.dom, pk.dom4
         A = pk.arena
         mark = A.mark()
         T = trace if trace is not None else {}
+        if public_inputs is None:
+            pi = pk.public_inputs
+        else:               # proof_system/pi.rs: zero values are not stored
+            pi = {int(k): int(v) % p for k, v in public_inputs.items() if int(v) % p}
+            if any(r < 0 or r >= n for r in pi):
+                raise ApbError(1, "public input row outside the circuit")
         try:
             return self._prove(pk, wires_mont, transcript_label, faithful, T, A, dom, dom4, n, N4, p, curve, lib,
-                               wires_resident)
+                               wires_resident, pi)
         finally:
             lib.c.apb_dev_sync()
             A.release(mark)
 
-    def _prove(self, pk, wires_mont, label, faithful, T, A, dom, dom4, n, N4, p, curve, lib, wires_resident=None):
+    def _prove(self, pk, wires_mont, label, faithful, T, A, dom, dom4, n, N4, p, curve, lib, wires_resident=None,
+               public_inputs=None):
+        public_inputs = pk.public_inputs if public_inputs is None else public_inputs
         tr = Transcript(lib, curve, label)
         # PublicInputs (proof_system/pi.rs) = BTreeMap<usize, F>: u64 length, (u64 row, element) in row order
-        pi_ser = len(pk.public_inputs).to_bytes(8, "little")
-        for pos in sorted(pk.public_inputs):
-            pi_ser += pos.to_bytes(8, "little") + pk.public_inputs[pos].to_bytes(32, "little")
+        pi_ser = len(public_inputs).to_bytes(8, "little")
+        for pos in sorted(public_inputs):
+            pi_ser += pos.to_bytes(8, "little") + public_inputs[pos].to_bytes(32, "little")
         tr.append_bytes(b"pi", pi_ser)
         omega = self._root_of_unity(n)
 
@@ -405,10 +416,10 @@ class Prover:
         var_sep = tr.challenge(b"variable base separation challenge"); tr.append_fr(b"variable base separation challenge", var_sep)
         lookup_sep = tr.challenge(b"lookup separation challenge"); tr.append_fr(b"lookup separation challenge", lookup_sep)
         pi_poly = None
-        if pk.public_inputs:                                                 # prover.rs:400 (pi_poly = ifft of the PI column)
+        if public_inputs:                                                    # prover.rs:392 (pi_poly = ifft of the PI column)
             pi_col = np.zeros((n, 4), dtype=np.uint64)
-            rows = sorted(pk.public_inputs)
-            pi_col[rows] = _mont_list(curve, [pk.public_inputs[r] for r in rows])
+            rows = sorted(public_inputs)
+            pi_col[rows] = _mont_list(curve, [public_inputs[r] for r in rows])
             pi_poly = A.alloc(n)
             A.upload(pi_poly, pi_col)
             self._ntt(dom, NTT_IFFT, A, pi_poly, n, pi_poly)
@@ -499,24 +510,24 @@ class Prover:
 
         # -- openings (prover.rs:563-618; sonic_pc::open: p = sum challenge^i p_i, witness = p / (X - z))
         aw_challenge = tr.challenge(b"aggregate_witness")
+        saw_challenge = tr.challenge(b"aggregate_witness")          # prover.rs:593: no absorb between the two challenges
         aw_polys = [lin_poly, P["left_sigma"], P["right_sigma"], P["out_sigma"], f_poly, h2_poly, table_poly] + wp
-        comb = A.alloc(n)
-        wit = A.alloc(n)
-        self._lincomb(A, aw_polys, [n] * len(aw_polys), [pow(aw_challenge, i, p) for i in range(len(aw_polys))], comb, n)
-        zc_m, zw_m = _mont(curve, zc), _mont(curve, zw)
-        lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb), n, zc_m.ctypes.data, A.ptr(wit)))
-        if faithful:       # PC::commit(aw_polys) (prover.rs:579, results unused by open) + the opening MSM, one pass
-            aw_open = self._commit(A, aw_polys[:7] + [wit], [n] * 7 + [n - 1])[7]
-        else:
-            aw_open = self._commit(A, [wit], [n - 1])[0]
-        saw_challenge = tr.challenge(b"aggregate_witness")
         saw_polys = [z_poly, wp[0], wp[1], wp[3], h1_poly, z2_poly, table_poly]
-        self._lincomb(A, saw_polys, [n] * 7, [pow(saw_challenge, i, p) for i in range(7)], comb, n)
-        lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb), n, zw_m.ctypes.data, A.ptr(wit)))
+        comb = A.alloc(2 * n)
+        wit = A.alloc(2 * n)
+        zc_m, zw_m = _mont(curve, zc), _mont(curve, zw)
+        self._lincomb(A, aw_polys, [n] * len(aw_polys), [pow(aw_challenge, i, p) for i in range(len(aw_polys))], comb, n)
+        lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb), n, zc_m.ctypes.data, A.ptr(wit)))
+        self._lincomb(A, saw_polys, [n] * 7, [pow(saw_challenge, i, p) for i in range(7)], comb + n, n)
+        lib.check(lib.c.apb_poly_divide_linear(curve, A.ptr(comb + n), n, zw_m.ctypes.data, A.ptr(wit + n)))
+        # The saw opening does not depend on the aw opening, so everything round 5 commits goes through ONE
+        # batched pass: PC::commit(aw_polys) and PC::commit(saw_polys) (prover.rs:579,606 - 7 + 7 commitments
+        # that SonicKZG10::open then ignores; issued when `faithful`) and the two opening MSMs (prover.rs:582,609).
         if faithful:
-            saw_open = self._commit(A, saw_polys + [wit], [n] * 7 + [n - 1])[7]
+            res = self._commit(A, aw_polys[:7] + [wit] + saw_polys + [wit + n], [n] * 7 + [n - 1] + [n] * 7 + [n - 1])
+            aw_open, saw_open = res[7], res[15]
         else:
-            saw_open = self._commit(A, [wit], [n - 1])[0]
+            aw_open, saw_open = self._commit(A, [wit, wit + n], [n - 1, n - 1])
 
         if T is not None and T.get("want"):
             T.update(zeta=zeta, beta=beta, gamma=gamma, delta=delta, epsilon=epsilon, alpha=alpha, lookup_sep=lookup_sep,

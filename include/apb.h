@@ -196,8 +196,13 @@ int apb_mul_bench(int field, int threads, int blocks_per_sm, int ilp, uint32_t i
  * (recorded only after apb_set_profiling(1)) */
 void apb_set_profiling(int on);
 void apb_msm_phase_ms(double out[4]);
+/* plan of the last MSM pass: {digit bits, batched-affine pair levels, bucket-range slices, 1 if it fell
+ * back to the plain accumulate because the slices were unbalanced} */
+void apb_msm_last_plan(uint32_t out[4]);
 /* totals since the last reset while profiling: k_msm_accumulate milliseconds and scalars processed */
 void apb_msm_totals(double* accumulate_ms, unsigned long long* points, int reset);
+/* device time of whole MSM calls (sort + accumulation + bucket reduction + copy-out + host epilogue) */
+void apb_msm_call_ms(double* whole_calls_ms, int reset);
 /* wide multiply-adds of the bucket accumulation stage since the last reset while profiling: by the
  * XYZZ cost model of SURVEY 8(d) (entries x 10 Fq products x 300) and as issued (6 products per
  * batched-affine pair addition, 10 per XYZZ mixed addition) */

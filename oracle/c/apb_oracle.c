@@ -492,3 +492,51 @@ void oracle_fr_from_mont(int curve, u64* data, size_t n) {
     u64 o[4] = {1, 0, 0, 0};
     for (size_t i = 0; i < n; i++) f_mul4(&FR[curve], data + 4 * i, data + 4 * i, o);
 }
+
+/* ---- polynomial evaluation (test checker): sum_i coeffs[i] * x^i over Fr, all values Montgomery ----
+ * DensePolynomial::evaluate of ark-poly (Horner); used by the tests as the size-independent check of
+ * large transforms (fft(p)[i] == p(w^i)) and of large MSMs over powers of tau (MSM == [p(tau)]G).
+ * Threads evaluate contiguous chunks by Horner and the chunk values are combined with x^(chunk start). */
+typedef struct {
+    const field_t* f;
+    const u64* c;
+    size_t lo, hi;
+    const u64* x;
+    u64 val[4];
+} horner_job_t;
+static void* horner_worker(void* arg) {
+    horner_job_t* J = (horner_job_t*)arg;
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t i = J->hi; i-- > J->lo;) {
+        f_mul4(J->f, acc, acc, J->x);
+        f_add(J->f, acc, acc, J->c + 4 * i);
+    }
+    memcpy(J->val, acc, 32);
+    return NULL;
+}
+/* coeffs: n x 4 u64 (Montgomery), x: 4 u64 (Montgomery) -> out: 4 u64 (Montgomery) */
+int oracle_fr_horner(int curve, const u64* coeffs, size_t n, const u64* x, int threads, u64* out) {
+    oracle_init();
+    const field_t* f = &FR[curve];
+    if (threads < 1) threads = 1;
+    if (n < 4096) threads = 1;
+    horner_job_t* jobs = (horner_job_t*)malloc(sizeof(horner_job_t) * threads);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+    for (int t = 0; t < threads; t++) {
+        jobs[t].f = f; jobs[t].c = coeffs; jobs[t].x = x;
+        jobs[t].lo = n * t / threads; jobs[t].hi = n * (t + 1) / threads;
+        if (threads > 1) pthread_create(&th[t], NULL, horner_worker, &jobs[t]);
+    }
+    if (threads == 1) horner_worker(&jobs[0]);
+    else for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    u64 acc[4] = {0, 0, 0, 0};
+    for (int t = threads; t-- > 0;) {           /* acc = acc * x^(len of chunk t) + val_t */
+        u64 e[4] = {jobs[t].hi - jobs[t].lo, 0, 0, 0}, xp[4];
+        f_pow(f, xp, x, e, 1);
+        f_mul4(f, acc, acc, xp);
+        f_add(f, acc, acc, jobs[t].val);
+    }
+    memcpy(out, acc, 32);
+    free(jobs); free(th);
+    return 0;
+}

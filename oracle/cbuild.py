@@ -35,6 +35,7 @@ def lib():
         _lib.oracle_ntt.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         _lib.oracle_fr_to_mont.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
         _lib.oracle_fr_from_mont.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+        _lib.oracle_fr_horner.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
         _lib.oracle_init()
     return _lib
 
@@ -60,3 +61,13 @@ def ntt(curve: int, kind: int, data_mont, log_n: int, threads: int = 1):
     if rc != 0:
         raise ValueError("oracle_ntt failed")
     return buf
+
+
+def fr_horner(curve: int, coeffs_mont, x_mont, threads: int = 1):
+    """sum_i coeffs[i] x^i over Fr: numpy (n,4) and (4,) uint64 Montgomery -> (4,) uint64 Montgomery."""
+    import numpy as np
+    c = np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4)
+    x = np.ascontiguousarray(x_mont, dtype=np.uint64).reshape(4)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_fr_horner(curve, c.ctypes.data, c.shape[0], x.ctypes.data, threads, out.ctypes.data)
+    return out

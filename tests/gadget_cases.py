@@ -113,3 +113,47 @@ def prove_gadget_case(lib, curve_id: int, kind: str, tamper: bool = False):
         return got
     assert got == want, "CUDA proof differs from the oracle's"
     return got
+
+
+def _pi_composer(curve_id: int, a: int, b: int, seed: int = 5):
+    """one structure, witness-dependent public inputs: and_gate(a, b) with PI = -(a & b), plus a range gate"""
+    curve = CURVES[curve_id]
+    rng = random.Random(seed)
+    cs = op.Composer(curve, [rng.randrange(curve.fr.p) for _ in range(8)])
+    cs.add_dummy_lookup_table()
+    r = cs.and_gate(cs.add_input(a), cs.add_input(b), 10)
+    cs.constrain_to_constant(r, 0, pi=-(a & b))
+    cs.range_gate(cs.add_input(a), 10)
+    return cs
+
+
+def prove_two_public_input_assignments(lib, curve_id: int = 0):
+    """ONE compiled key, TWO witnesses with different public inputs (the reference keeps PI out of the
+    ProverKey and reads them per proof: prover.rs:182,392; circuit.rs gen_proof): both proofs equal the
+    oracle's byte for byte and verify against their own public inputs, not against the other's"""
+    curve = CURVES[curve_id]
+    tau = random.Random(78).randrange(curve.fr.p)
+    cases = [(469, 321), (1000, 731)]
+    comps = [_pi_composer(curve_id, a, b) for a, b in cases]
+    circs = [arrays_from_composer(cs, curve_id) for cs in comps]
+    n = comps[0].circuit_bound()
+    assert comps[1].circuit_bound() == n and comps[0].public_inputs != comps[1].public_inputs
+    ck = kzg.CommitterKey.from_tau(curve_id, tau, n + 1, lib=lib)
+    pr = gp.Prover(curve_id, ck, lib=lib)
+    pk = pr.preprocess(circs[0], commit_verifier_key=True)                 # compiled once, from the first witness
+    try:
+        for cs, circ in zip(comps, circs):
+            pis = dict(cs.public_inputs)
+            okzg = op.Kzg(curve, tau, n + 8)
+            opk = op.preprocess(cs, okzg)
+            for name, comp in pk.commitments.items():                      # structure only: same verifier key
+                assert comp == op.ser_g1(curve, opk.commitments[name]), name
+            _, want = op.prove(cs, opk, okzg, b"pi")
+            got = pr.prove(pk, gp.wires_to_mont(circ), b"pi", public_inputs=pis)
+            assert got == want
+            assert pv.verify(curve, opk.commitments, n, got, tau, b"pi", public_inputs=pis)
+            other = comps[1].public_inputs if cs is comps[0] else comps[0].public_inputs
+            assert not pv.verify(curve, opk.commitments, n, got, tau, b"pi", public_inputs=other)
+    finally:
+        pk.arena.close()
+        ck.close()

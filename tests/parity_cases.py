@@ -218,3 +218,34 @@ def check_kzg_open_and_domain_helpers(lib, curve, log_n, seed=12):
         assert d.evaluate_all_lagrange_coefficients(od.element(5 % n))[5 % n] == 1
     finally:
         d.close()
+
+
+def check_msm_pass_split(lib, curve=0, n=48, k=4, limit_split=4000, limit_fail=1000, seed=21, **envkw):
+    """the bucket-entry list of one pass has 32-bit positions: a batch above the bound is split into
+    several passes (same results), a single polynomial above it is refused (APB_MSM_MAX_ENTRIES lowers
+    the bound so that small inputs reach both paths)"""
+    from ark_plonk_b200._lib import ApbError
+    cv = CURVES[curve]
+    rnd = random.Random(seed)
+    a, b = rnd.randrange(1, cv.fr.p), rnd.randrange(1, cv.fr.p)
+    pts = synth.progression_bases(curve, a, b, n)
+    ck = kzg.CommitterKey(curve, enc.g1_affine_to_mont(curve, pts), lib=lib)
+    try:
+        polys, expect = [], []
+        for j in range(k):
+            s = [rnd.randrange(cv.fr.p) for _ in range(n - j)]
+            polys.append(enc.fr_to_mont(curve, s))
+            expect.append(synth.progression_expected(curve, a, b, s))
+        with env(APB_MSM_MAX_ENTRIES=limit_split, **envkw):
+            outs = kzg.commit(ck, polys)
+        for out, exp in zip(outs, expect):
+            assert enc.g1_from_xyz(curve, out) == exp
+        with env(APB_MSM_MAX_ENTRIES=limit_fail, **envkw):
+            try:
+                kzg.commit(ck, polys)
+            except ApbError as e:
+                assert e.code == 1
+            else:
+                raise AssertionError("a pass above the 32-bit entry bound must be refused")
+    finally:
+        ck.close()

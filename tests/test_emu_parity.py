@@ -130,3 +130,8 @@ def test_error_behaviour(emu_lib):
     z = d.fft(np.zeros((0, 4), dtype=np.uint64))                    # empty polynomial -> N zeros (coset_fft of q_range etc.)
     assert z.shape == (8, 4) and not z.any()
     d.close()
+
+
+def test_msm_pass_split_at_the_entry_bound(emu_lib):
+    # c = 8: 32 digit positions, 2 windows of 128 buckets per polynomial -> 48 x 32 + 256 entries each
+    pc.check_msm_pass_split(emu_lib, 0, n=48, k=4, limit_split=4000, limit_fail=1000, APB_MSM_C=8, APB_MSM_CHUNK=5)

@@ -18,3 +18,7 @@ def test_prover_custom_gates_match_oracle(emu_lib, curve, kind):
     """range / logic / curve-addition / fixed-base gate terms and public inputs (quotient_poly.rs:231-264,
     linearisation_poly.rs:382-410): the proof equals the oracle's byte for byte and verifies"""
     gadget_cases.prove_gadget_case(emu_lib, curve, kind)
+
+
+def test_one_key_two_public_input_assignments(emu_lib):
+    gadget_cases.prove_two_public_input_assignments(emu_lib, 0)

@@ -83,24 +83,19 @@ def _prove_worker(rank, world, port, emu_path, result_q):
     tau = int(case["tau"], 16)
     circ = bc.build(0, 5, [int(b, 16) for b in case["blinders"]])
     ck = kzg.CommitterKey.from_tau(0, tau, circ.n + 1, lib=lib)
-    com = parallel.DistributedCommitter(0, ck, circ.n, group=None, device="cpu", lib=lib)
-    ok, served = True, 0
-    if rank == 0:
-        pr = gp.Prover(0, ck, lib=lib, committer=com, arena_device="cpu")
-        pk = pr.preprocess(circ, commit_verifier_key=False)
-        blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")
-        ok = hashlib.sha256(blob).hexdigest() == case["proof_sha256"]
-        com.shutdown()
-    else:
-        served = com.serve()
-        ok = served == 6                      # the prover issues 6 batched commit calls per proof
+    com = parallel.DistributedCommitter(0, ck, group=None, device="cpu", lib=lib)
+    # SPMD: every rank runs the whole prover; each commit batch is split evenly, 144-byte partials all-reduced
+    pr = gp.Prover(0, ck, lib=lib, committer=com)
+    pk = pr.preprocess(circ, commit_verifier_key=False)
+    blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")
+    ok = hashlib.sha256(blob).hexdigest() == case["proof_sha256"] and com.batches == 5   # 5 batched commit calls per proof
     result_q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
 def test_prove_with_commitments_split_over_two_ranks(emu_lib):
-    """batched prove: rank 0 proves, rank 1 serves half of the polynomials of every commit batch; the proof is
-    byte-identical to the golden vector"""
+    """batched prove, SPMD: both ranks run the prover, each multiplies half of the points of every commit batch;
+    the proof is byte-identical to the golden vector on BOTH ranks"""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -131,25 +126,24 @@ def _commit_split_worker(rank, world, port, emu_path, result_q):
     n = 29
     pts = synth.progression_bases(0, 3, 7, n)
     ck = kzg.CommitterKey(0, enc.g1_affine_to_mont(0, pts), lib=lib)
-    com = parallel.DistributedCommitter(0, ck, n, k_max=4, device="cpu", lib=lib)
+    com = parallel.DistributedCommitter(0, ck, k_max=4, device="cpu", lib=lib)
     ok = True
-    if rank == 0:
-        arena = Arena(lib, 8 * n, torch_device="cpu")
-        rnd = random.Random(5)
-        polys = [[rnd.randrange(enc.FR_MODULUS[0]) for _ in range(ln)] for ln in (n, n - 1, 7)]
-        offs = []
-        for q in polys:
-            o = arena.alloc(n)
+    arena = Arena(lib, 8 * n)
+    rnd = random.Random(5)
+    polys = [[rnd.randrange(enc.FR_MODULUS[0]) for _ in range(ln)] for ln in (n, n - 1, 7, 0, n, 3)]
+    offs = []
+    for q in polys:
+        o = arena.alloc(n)
+        if q:
             arena.upload(o, enc.fr_to_mont(0, q))
-            offs.append(o)
-        # k = 1 < world: the single polynomial is point-split over both ranks; k = 3 >= world: round robin
-        for sel in ([0], [1], [0, 1, 2]):
-            out = com.commit(arena, [offs[i] for i in sel], [len(polys[i]) for i in sel])
-            for row, i in zip(out, sel):
-                ok = ok and enc.g1_from_xyz(0, row) == synth.progression_expected(0, 3, 7, polys[i])
-        com.shutdown()
-    else:
-        ok = com.serve() == 3
+        offs.append(o)
+    # k = 1 < world: the polynomial is point-split; k = 3: cut across a polynomial border; k = 6 > k_max: two rounds
+    for sel in ([0], [1], [0, 1, 2], [0, 1, 2, 3, 4, 5]):
+        out = com.commit(arena, [offs[i] for i in sel], [len(polys[i]) for i in sel])
+        for row, i in zip(out, sel):
+            ok = ok and enc.g1_from_xyz(0, row) == synth.progression_expected(0, 3, 7, polys[i])
+    ok = ok and parallel.split_pieces([10, 10, 10], 2) == [(0, 0, 10, 0), (1, 0, 5, 0), (1, 5, 10, 1), (2, 0, 10, 1)]
+    arena.close()
     result_q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -37,3 +37,15 @@ def test_c_msm_matches_tau_identity():
             got = None if out is None else tuple(enc.fq_from_mont(curve, out.reshape(2, 6)))
             assert got == exp, (curve, n)
             assert exp == cv.msm_pippenger(pts, s)
+
+
+def test_c_horner_matches_python_oracle():
+    from oracle.ntt import poly_eval
+    rnd = random.Random(5)
+    for curve in (0, 1):
+        f = FR[curve]
+        for n, threads in ((0, 1), (1, 1), (100, 1), (5000, 3), (10000, 8)):
+            c = [rnd.randrange(f.p) for _ in range(n)]
+            x = rnd.randrange(f.p)
+            got = cbuild.fr_horner(curve, enc.fr_to_mont(curve, c) if n else [], enc.fr_to_mont(curve, [x])[0], threads=threads)
+            assert enc.fr_from_mont(curve, got.reshape(1, 4)) == [poly_eval(f, c, x)], (curve, n)
