@@ -264,11 +264,29 @@ struct TreeJob {
 };
 
 template <class FQ>
+APB_D XYZZ<FQ> shfl_down_xyzz(const XYZZ<FQ>& a, uint32_t delta) {
+    XYZZ<FQ> r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < FQ::N; i++) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, a.x.v[i], delta);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, a.y.v[i], delta);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, a.zz.v[i], delta);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, a.zzz.v[i], delta);
+    }
+#else
+    (void)delta;
+    r = a;
+#endif
+    return r;
+}
+
+template <class FQ>
 __global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, const TreeJob* jobs, uint32_t njobs) {
-    // one job per warp (4 per CTA): every lane first folds m/32 strided elements sequentially, then
-    // a 5-level tree inside the warp through shared memory.  13 dependent additions for a
-    // 256-element job with 61 % of the lanes busy (the former CTA-wide tree: 9 deep but 22 %).
-    __shared__ uint4 sm[128 * 12];       // 128 XYZZ points (4 * 48 bytes), 32 per warp
+    // one job per warp (4 per CTA): every lane first folds m/32 strided elements sequentially, then a
+    // 5-level tree inside the warp.  On the device the tree exchanges points with register shuffles: no
+    // shared memory and no CTA barrier (round 1 went through shared memory with two __syncthreads per
+    // level, which cost 10 barrier-stall cycles per issued instruction: profiles/r01_ncu_prove_kernels.json).
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t job = blockIdx.x * 4 + (tid >> 5);
     const bool active = job < njobs;
@@ -281,6 +299,14 @@ __global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, con
         XYZZ<FQ> p = load_xyzz<FQ>(in, (uint64_t)J.base + (uint64_t)e * J.stride);
         acc.add(p);
     }
+#ifndef APB_EMU
+    for (uint32_t s = 16; s >= 1; s >>= 1) {
+        const XYZZ<FQ> p = shfl_down_xyzz<FQ>(acc, s);
+        if (lane < s) acc.add(p);
+    }
+#else
+    // CPU emulation (one OS thread per CUDA thread, no lockstep warps): the same tree through shared memory
+    __shared__ uint4 sm[128 * 12];       // 128 XYZZ points (4 * 48 bytes), 32 per warp
     store_xyzz<FQ>(sm, tid, acc);
     __syncthreads();
     for (uint32_t s = 16; s >= 1; s >>= 1) {
@@ -292,6 +318,7 @@ __global__ void __launch_bounds__(128) k_msm_tree(const void* in, void* out, con
         if (lane < s) store_xyzz<FQ>(sm, tid, acc);
         __syncthreads();
     }
+#endif
     if (active && lane == 0) store_xyzz<FQ>(out, J.out, acc);
 }
 
