@@ -285,6 +285,59 @@ class Prover:
         lib.check(lib.c.apb_dev_sync())
         return pk
 
+    def load_prover_key(self, blob: bytes) -> ProverKey:
+        """`ProverKey::deserialize_unchecked` (proof_system/widget/mod.rs:285-328; circuit.rs:264-268 takes such a
+        key by value): builds the device-resident key from arkworks' serialized form instead of compiling the
+        circuit.  Residents the reference recomputes per proof (L1 evaluations, q_lookup on the n-domain, 1/Z_H)
+        are derived here once.  Public inputs are not part of the key: pass them to `prove`."""
+        from . import serialize as ser
+        curve, p, lib = self.curve, self.p, self.lib
+        arr = ser.read_prover_key_arrays(curve, blob)
+        n = arr["n"]
+        field_id = 0 if curve == 0 else 2
+
+        def mont(a):
+            a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+            return lib.field_op(field_id, 3, a, None) if a.shape[0] else a
+
+        custom = tuple(s for s in CUSTOM_SELECTORS if arr["poly"][s].shape[0])
+        dom = Radix2EvaluationDomain(curve, n, lib=lib)
+        dom4 = Radix2EvaluationDomain(curve, 4 * n, lib=lib)
+        names = [s for s in SELECTORS if s not in CUSTOM_SELECTORS or s in custom]
+        sig_names = ["left_sigma", "right_sigma", "out_sigma", "fourth_sigma"]
+        arena = Arena(lib, (len(names) + 4 + 4 + 1 + 6 + 36) * n + (len(names) + 4 + 2 + 12) * 4 * n,
+                      torch_device=self.arena_device)
+        pk = ProverKey(curve=curve, n=n, arena=arena, dom=dom, dom4=dom4, custom=custom, public_inputs={})
+        for s in names + sig_names:
+            c = np.zeros((n, 4), dtype=np.uint64)
+            m = mont(arr["poly"][s])
+            c[: m.shape[0]] = m
+            pk.poly[s] = arena.alloc(n)
+            arena.upload(pk.poly[s], c)
+            pk.ev4[s] = arena.alloc(4 * n)
+            arena.upload(pk.ev4[s], mont(arr["ev4"][s]))
+        pk.q_lookup_evals = arena.alloc(n)
+        self._ntt(dom, NTT_FFT, arena, pk.poly["q_lookup"], n, pk.q_lookup_evals)
+        pk.tables = []
+        for t in arr["tables"]:
+            off = arena.alloc(n)
+            arena.upload(off, mont(t))
+            pk.tables.append(off)
+        pk.ev4["linear"] = arena.alloc(4 * n)
+        arena.upload(pk.ev4["linear"], mont(arr["linear"]))
+        tmp = arena.alloc(n)
+        l1 = np.zeros((n, 4), dtype=np.uint64)
+        l1[0] = _mont(curve, 1)
+        arena.upload(tmp, l1)
+        l1_poly = arena.alloc(n)
+        self._ntt(dom, NTT_IFFT, arena, tmp, n, l1_poly)
+        pk.ev4["l1"] = arena.alloc(4 * n)
+        self._ntt(dom4, NTT_COSET_FFT, arena, l1_poly, n, pk.ev4["l1"])
+        vh = enc.limbs_to_ints(arr["v_h"][:4])
+        pk.vh_inv = _mont_list(curve, [pow(v, -1, p) for v in vh])
+        lib.check(lib.c.apb_dev_sync())
+        return pk
+
     def _root_of_unity(self, size: int) -> int:
         p = self.p
         adicity = 32 if self.curve == 0 else 47

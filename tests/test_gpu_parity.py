@@ -202,3 +202,26 @@ def test_ntt_roundtrip_on_device_large(gpu_lib, log_n):
     d.close()
     del x, y
     torch.cuda.empty_cache()
+
+
+# ---- ark-serialize wire formats (reference serde tests widget/mod.rs:438-572) -----------------
+import serialize_cases  # noqa: E402
+
+
+def test_serialize_srs_powers_roundtrip(gpu_lib):
+    serialize_cases.check_srs_roundtrip(gpu_lib, 0, n=300)
+    serialize_cases.check_srs_roundtrip(gpu_lib, 1, n=100)
+
+
+@pytest.mark.parametrize("curve,degree", [(0, 11), (1, 10)])
+def test_serialize_prover_and_verifier_key_roundtrip(gpu_lib, curve, degree):
+    """n = 2^11 as in the reference's test_serialise_deserialise_prover_key; the reloaded key proves to the same bytes"""
+    if (curve, degree) == (0, 11):
+        from ark_plonk_b200 import bench_circuit as bc
+        prover_cases.GOLDEN.append({"curve": 0, "degree": 11, "tau": hex(0x5EED11), "blinders": [hex(90 + i) for i in range(8)],
+                                    "proof": None})
+    serialize_cases.check_keys_roundtrip(gpu_lib, curve, degree)
+
+
+def test_serialize_key_roundtrip_custom_gates(gpu_lib):
+    serialize_cases.check_keys_roundtrip(gpu_lib, 0, kind="mixed")
