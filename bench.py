@@ -598,294 +598,6 @@ def run_b200(args):
                                     "sample": "arkworks-algorithm VariableBaseMSM (oracle/c) over 2^%d points, %.1f s" % (min(log_n, 15), dt)}
     else:
         log_n = args.log_n or 20
-        log_sample = min(log_n, 18)
-        for i in range(args.warmup + args.steps):
-            v, dt = cpu_ntt_baseline(log_sample, cores)
-            if i >= args.warmup:
-                vals.append(v)
-                times.append(dt)
-        metric, unit = "ntt_gb_per_s", "GB/s"
-        workload = "coset FFT, BLS12-381 Fr, 2^%d elements per GPU" % log_n
-        sample = "coset_fft of 2^%d elements per step" % log_sample
-    value = float(np.mean(vals))
-    line = {
-        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb integers", "data": "synthetic",
-        "config": {"workload": workload, "curve": "BLS12-381"},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "arkworks-0.3-algorithm restatement in C (oracle/c); the Rust reference cannot be built here",
-    }
-    print(json.dumps(line), flush=True)
-
-
-# --------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-
-    from ark_plonk_b200 import encoding as enc
-    from ark_plonk_b200 import kzg, synth
-    from ark_plonk_b200._lib import get_lib
-    from ark_plonk_b200.domain import Radix2EvaluationDomain
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = get_lib()
-    lib.init(local)
-    stream = torch.cuda.ExternalStream(lib.c.apb_stream())
-    K, W = args.steps, args.warmup
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    wide_peak, imad32_peak = lib.imad_peak()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-
-    line = {}
-    if args.workload == "prove":
-        import hashlib
-
-        from ark_plonk_b200 import bench_circuit as bc
-        from ark_plonk_b200 import plonk as gp
-        log_n = args.log_n or 18
-        split = args.prove_mode == "split"           # one proof over all ranks (SPMD); at N = 1 the same single proof
-        salt = 0 if split else rank
-        tau = 0x1234567890ABCDEF1234567890ABCDEF + salt
-        circ = bc.build(0, log_n, [1000 + 8 * salt + i for i in range(8)])
-        n = circ.n
-        ck = kzg.CommitterKey.from_tau(0, tau, n + 1)
-        committer = None
-        if split and world > 1:
-            from ark_plonk_b200 import parallel
-            committer = parallel.DistributedCommitter(0, ck, device="cuda")
-        pr = gp.Prover(0, ck, committer=committer)
-        pk = pr.preprocess(circ, commit_verifier_key=False)
-        wires = gp.wires_to_mont(circ)
-        wires_pinned = torch.from_numpy(wires.view(np.int64)).pin_memory()
-        w_res = pr.upload_wires(pk, wires)
-        lib.set_profiling(True)
-        proof = None
-        for _ in range(W):
-            proof = pr.prove(pk, None, b"ark", wires_resident=w_res)
-        sampler = ClockSampler(local)
-        sampler.start()
-        lib.msm_totals(reset=True)
-        lib.msm_work(reset=True)
-        lib.msm_call_ms(reset=True)
-        launches0 = lib.kernel_launches()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record()
-        for _ in range(K):
-            proof = pr.prove(pk, None, b"ark", wires_resident=w_res)
-        with torch.cuda.stream(stream):
-            e1.record()
-        barrier()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = lib.kernel_launches() - launches0
-        acc_total_ms, pts_total = lib.msm_totals()
-        madds_model, madds_issued = lib.msm_work()
-        msm_calls_ms = lib.msm_call_ms()
-        clocks = sampler.result()
-        ms_per_step = total_ms / K
-        # end to end: pinned host witness in, proof bytes out
-        for _ in range(W):
-            proof_e2e = pr.prove(pk, wires_pinned.data_ptr(), b"ark")
-        assert proof_e2e == proof
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            proof_e2e = pr.prove(pk, wires_pinned.data_ptr(), b"ark")
-        barrier()
-        e2e_local = (time.perf_counter() - t0) * 1e3
-        # per-phase split of one profiled proof (outside the timed regions): MSM / NTT / other
-        lib.ntt_totals(reset=True)
-        pr.phase_log = []
-        barrier()
-        t0 = time.perf_counter()
-        pr.prove(pk, None, b"ark", wires_resident=w_res)
-        prof_ms = (time.perf_counter() - t0) * 1e3
-        log, pr.phase_log = pr.phase_log, None
-        msm_ms = sum(m for _, m, _ in log)
-        ntt_ms, ntt_cnt = lib.ntt_totals()
-        phase_split = {"msm_ms": msm_ms, "ntt_ms": ntt_ms, "other_ms": max(prof_ms - msm_ms - ntt_ms, 0.0), "profiled_proof_ms": prof_ms,
-                       "msm_calls": len(log), "msm_count": sum(k for k, _, _ in log), "ntt_transforms": int(ntt_cnt),
-                       "msm_accumulate_ms": sum(p["accumulate"] for _, _, p in log), "msm_sort_ms": sum(p["sort"] for _, _, p in log),
-                       "msm_reduce_ms": sum(p["reduce"] for _, _, p in log)}
-        # extra (not the headline): the same proof without the 14 commitments whose results the reference discards
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(max(K // 2, 1)):
-            proof_nd = pr.prove(pk, None, b"ark", wires_resident=w_res, faithful=False)
-        barrier()
-        no_dead_ms = (time.perf_counter() - t0) * 1e3 / max(K // 2, 1)
-        assert proof_nd == proof
-        e2e_ms = max_over_ranks(e2e_local) / K
-        sha = hashlib.sha256(proof).hexdigest()
-        golden_match = None                      # the oracle's proof of this exact instance (tools/gen_golden_2p18.py)
-        gpath = os.path.join(ROOT, "tests", "golden", "plonk_bench_2p%d.json" % log_n)
-        if salt == 0 and os.path.exists(gpath):
-            golden_match = json.load(open(gpath))["proof_sha256"] == sha
-            assert golden_match, "proof differs from the oracle's golden proof of the bench instance"
-        stage_s = acc_total_ms * 1e-3
-        achieved = pts_total * MSM_IMAD_PER_POINT / stage_s / 1e12
-        ncalls = max(len(log), 1)
-        acc_per_launch = acc_total_ms / (K * ncalls)
-        line = {
-            "metric": "plonk_prove_ms", "value": ms_per_step, "unit": "ms", "ms_per_step": ms_per_step, "higher_is_better": False,
-            "scaling": "strong" if split else "weak",
-            "vs_baseline": ms_per_step / 20184.0 if log_n == 18 else None,
-            "config": {"workload": "BLS12-381 KZG10 prove, BenchCircuit 2^%d gates (with lookups), %d real rows" % (log_n, circ.rows),
-                       "curve": "BLS12-381", "msm_per_proof": 29, "ntt_n_per_proof": 17, "ntt_4n_per_proof": 11,
-                       "multi_gpu": ("one proof, SPMD over %d ranks: every rank runs the prover, the points of each of the %d commit "
-                                     "batches are split evenly, one all-reduce of 144-byte partial sums per batch" % (world, ncalls))
-                                    if split and world > 1 else ("%d independent proofs" % world if world > 1 else "single GPU"),
-                       "proof_sha256": sha, "golden_match": golden_match,
-                       "extra_ms_without_discarded_commitments": no_dead_ms,
-                       "phase_split_of_one_profiled_proof": phase_split,
-                       "l2": "inputs exceed L2 (resident key table %d MB, prover key %d MB)" % ((n + 1) * 16 * 96 >> 20, pk.arena.elems * 32 >> 20),
-                       "vs_baseline_note": "this value / published 20184 ms (Ryzen 7 3700X CPU, reference README.md:107); < 1 is faster"},
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": len(proof) + 29 * 3024},
-            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels) + k_msm_accumulate (XYZZ)",
-                         "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
-                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12),
-                         "frac_whole_msm": pts_total * MSM_IMAD_PER_POINT / (msm_calls_ms * 1e-3) / wide_peak if msm_calls_ms else None,
-                         "frac_whole_step": pts_total * MSM_IMAD_PER_POINT / (total_ms * 1e-3) / wide_peak,
-                         "traffic": ncu_traffic("k_msm_", per="k_msm_accumulate", capture=NCU_STAGE_CAPTURE),
-                         "issued": {"achieved": madds_issued / stage_s / 1e12,
-                                    "frac": madds_issued / stage_s / wide_peak,
-                                    "issued_over_model": madds_issued / madds_model if madds_model else None,
-                                    "note": "multiply-adds actually issued: a batched-affine pair addition costs 6 Fq products, the XYZZ "
-                                            "mixed addition of the cost model 10; `achieved`/`frac` keep SURVEY 8(d)'s algorithmic figure"},
-                         "traffic_note": "DRAM bytes of the stage (pair levels + accumulate) per commit call, ncu --set full (profiles/%s); "
-                                         "algorithmic bytes per call = entries x (4 B id + 96 B point) = %.2e (mean of the %d calls)" % (
-                                             NCU_STAGE_CAPTURE, pts_total / K * 16 * 100 / ncalls, ncalls),
-                         "kernel_ms_per_launch": acc_per_launch, "launches_per_step": ncalls,
-                         "kernel_share_of_step": acc_total_ms / K / ms_per_step,
-                         "whole_msm_ms_per_step": msm_calls_ms / K,
-                         "frac_note": "peak = independent (carry-free) IMAD.WIDE chains; the carry-chained IMAD.WIDE.X of a Montgomery product "
-                                      "issues at half that rate, so 0.5 is the ceiling of THIS carry-chain formulation (not of the chip); "
-                                      "`frac` times the accumulation stage only, `frac_whole_msm` all MSM calls (sort, reduction, copy-out, "
-                                      "host epilogue included), `frac_whole_step` the whole proof",
-                         "peak_source": "measured live: independent mad.wide.u32 chains (apb_imad_peak)",
-                         "note": "algorithmic 48000 wide multiply-adds per point x %d points per proof (SURVEY 8d)" % (pts_total // K)},
-        }
-        if rank == 0:
-            v, parts = cpu_prove_schedule(log_n, host_cores())
-            line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": host_cores(), "kind": "port",
-                                    "sample": cpu_prove_sample_text(log_n, parts)}
-    elif args.workload == "msm":
-        log_n = args.log_n or 18
-        n = 1 << log_n
-        # rank r owns points [r*n, (r+1)*n) of a (world*n)-point MSM: P_i = [a + i b]G
-        a, b = 12345, 67891
-        pts = synth.progression_bases(0, a + rank * n * b, b, n)
-        ck = kzg.CommitterKey(0, enc.g1_affine_to_mont(0, pts))
-        S = synth.seeded_scalars(0, n, seed=b"bench%d" % rank)
-        dS = torch.from_numpy(S.view(np.int64)).cuda()
-        S_pinned = torch.from_numpy(S.view(np.int64)).pin_memory()
-        out = np.zeros(18, dtype=np.uint64)
-        gathered = torch.zeros(world * 18, dtype=torch.int64, device="cuda") if world > 1 else None
-
-        def fold():             # exchange the 144-byte partial sums; every rank folds them on the host
-            mine = torch.from_numpy(out.view(np.int64)).cuda()
-            dist.all_gather_into_tensor(gathered, mine)
-            parts = gathered.cpu().numpy().view(np.uint64).reshape(world, 18)
-            acc = parts[0]
-            for r in range(1, world):
-                acc = lib.g1_add(0, acc, parts[r])
-            return acc
-
-        def step_dev():
-            lib.check(lib.c.apb_msm_dev(ck._h, 0, dS.data_ptr(), n, 0, out.ctypes.data))
-            return fold() if world > 1 else out
-
-        def step_e2e():
-            lib.check(lib.c.apb_msm(ck._h, 0, S_pinned.data_ptr(), n, 0, out.ctypes.data))
-            return fold() if world > 1 else out
-
-        lib.set_profiling(True)
-        for _ in range(W):
-            step_dev()
-        # correctness of this rank's partial sum (closed form), outside the timed region
-        exp = synth.progression_expected(0, a + rank * n * b, b, synth.limbs_to_int_list(S))
-        assert enc.g1_from_xyz(0, out) == exp, "MSM result mismatch"
-        sampler = ClockSampler(local)
-        sampler.start()
-        launches0 = lib.kernel_launches()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        acc_ms = []
-        with torch.cuda.stream(stream):
-            e0.record()
-        for _ in range(K):
-            step_dev()
-            acc_ms.append(lib.msm_phase_ms()["accumulate"])
-        with torch.cuda.stream(stream):
-            e1.record()
-        barrier()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = lib.kernel_launches() - launches0
-        clocks = sampler.result()
-        ms_per_step = total_ms / K
-        value = world * n / (ms_per_step * 1e-3) / 1e6
-        # end to end through the blocking C-ABI call with host scalars
-        for _ in range(W):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            step_e2e()
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
-        acc = float(np.mean(acc_ms))
-        achieved = n * MSM_IMAD_PER_POINT / (acc * 1e-3) / 1e12
-        line = {
-            "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "ms_per_step": ms_per_step,
-            "config": {"workload": "KZG10 commitment MSM, BLS12-381 G1, 2^%d points per GPU" % log_n,
-                       "curve": "BLS12-381", "points_per_gpu": n, "digit_bits": 16, "precomputed_copies": 16,
-                       "l2": "inputs exceed L2 (resident base table %d MB)" % (n * 16 * 96 >> 20)},
-            "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32,
-                    "d2h_bytes_per_step": 144 + 15 * 192},
-            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels, lists >= 6 M entries) + "
-                                   "k_msm_accumulate (XYZZ)",
-                         "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
-                         "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12), "traffic": None,
-                         "kernel_ms": acc, "kernel_share_of_step": acc / ms_per_step,
-                         "peak_source": "measured live: independent mad.wide.u32 chains (apb_imad_peak)",
-                         "note": "algorithmic 48000 wide multiply-adds per point (SURVEY 8d: XYZZ cost model); carry-chained "
-                                 "IMAD.WIDE.X issues at half the plain IMAD.WIDE rate, so 0.5 is the ceiling of a pure XYZZ "
-                                 "accumulation - the pair levels issue 6 products per addition instead of 10 and can exceed it"},
-        }
-        if rank == 0 and world == 1:
-            v, dt = cpu_msm_baseline(min(log_n, 15), host_cores(), b"cpu")
-            line["cpu_baseline"] = {"value": v, "unit": "Mpts/s", "cores": host_cores(), "kind": "port",
-                                    "sample": "arkworks-algorithm VariableBaseMSM (oracle/c) over 2^%d points, %.1f s" % (min(log_n, 15), dt)}
-    else:
-        log_n = args.log_n or 20
         n = 1 << log_n
         dom = Radix2EvaluationDomain(args.curve, n)
         x = torch.randint(0, 2 ** 62, (n, 4), dtype=torch.int64, device="cuda")
