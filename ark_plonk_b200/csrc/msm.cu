@@ -587,6 +587,222 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs(const uint32_t* entries
     }
 }
 
+// ---- the same pair level with asynchronous shared-memory staging (cp.async) ----------------------------------
+// k_msm_pairs keeps its software pipeline in REGISTERS (the operands of the next output are loaded into a
+// second register set while the current addition runs): 214 registers, 2 CTAs = 8 warps per SM, and ncu showed
+// the kernel latency-bound (issue-active 28 %, long-scoreboard stalls on the 96-byte gathers).  Here the
+// operands of the next step are fetched by cp.async (LDGSTS: global -> shared memory, no register in between)
+// into a per-thread slot of a two-stage ring, and read back with LDS right where they are used: the prefetch
+// costs no registers, so three CTAs per SM fit without spills, and the gather latency is covered by a whole
+// step of arithmetic of 12 warps instead of 8.  A slot is private to its thread (only the thread that issued
+// the copies reads them), so cp.async.wait_group orders everything and no CTA barrier is needed in the loops.
+// Slot layout: chunk c (16 bytes) of thread t at uint4 index (stage * PAIR_CHUNKS + c) * 128 + t: consecutive
+// lanes touch consecutive 16-byte words, i.e. conflict-free LDS.128 / LDGSTS.128.
+static const int PAIR_CHUNKS = 15;           // x1 y1 x2 y2 prefix: 5 x 48 bytes
+static const int PAIR_STAGES = 2;
+static const size_t PAIR_SMEM_BYTES = (size_t)PAIR_STAGES * PAIR_CHUNKS * 128 * 16;
+
+APB_D void cp_async16(uint4* smem_dst, const uint4* gsrc) {
+#ifdef __CUDA_ARCH__
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+#else
+    *smem_dst = *gsrc;
+#endif
+}
+APB_D void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+APB_D void cp_async_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// 48-byte field element: global -> chunks [c0, c0 + 3) of this thread's slot
+template <class FQ>
+APB_D void stage_fp(uint4* slot, int c0, const void* base, uint64_t idx) {
+    const uint4* g = reinterpret_cast<const uint4*>(base) + idx * (FQ::N / 4);
+#pragma unroll
+    for (int i = 0; i < FQ::N / 4; i++) cp_async16(slot + (size_t)(c0 + i) * 128, g + i);
+}
+template <class FQ>
+APB_D Fp<FQ> unstage_fp(const uint4* slot, int c0) {
+    Fp<FQ> r;
+#pragma unroll
+    for (int i = 0; i < FQ::N / 4; i++) {
+        const uint4 t = slot[(size_t)(c0 + i) * 128];
+        r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+    }
+    return r;
+}
+
+template <class FQ, int FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_pairs2(const uint32_t* entries, const void* src, const uint32_t* off_in,
+                                                          const uint32_t* off_out, uint32_t nbuckets, uint32_t E, void* dst,
+                                                          void* prefix, uint2* stash) {
+    typedef Fp<FQ> F;
+    APB_DYN_SMEM(smem_raw);
+    uint4* sm = reinterpret_cast<uint4*>(smem_raw);      // staging ring; its head doubles as the product tree
+    const uint32_t tid = threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + tid;
+    const uint64_t Mout = off_out[nbuckets];
+    const uint64_t j0 = t * E < Mout ? t * E : Mout;
+    const uint64_t j1 = j0 + E < Mout ? j0 + E : Mout;
+    uint4* const ring = sm + tid;
+    const size_t stage_words = (size_t)PAIR_CHUNKS * 128;
+
+    // pass 1 (forward): denominators x2 - x1 and running prefix products, two outputs per stage
+    F run = F::one();
+    if (j0 < j1) {
+        PairWalker W;
+        W.init(off_in, off_out, nbuckets, j0);
+        const uint64_t ngroups = (j1 - j0 + 1) / 2;
+        uint2 idc[2], idn[2];                             // ids of the group being staged / of the one after it
+        auto fetch_ids = [&](uint2* id, uint64_t g) {
+            const uint64_t j = j0 + 2 * g;
+#pragma unroll
+            for (int q = 0; q < 2; q++) id[q] = j + q < j1 ? W.template next<FIRST>(entries, j + q) : make_uint2(0, NO_PARTNER);
+        };
+        auto issue = [&](const uint2* id, uint32_t stage) {
+            uint4* slot = ring + stage * stage_words;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (id[q].y != NO_PARTNER) {
+                    stage_fp<FQ>(slot, 6 * q, src, 2 * (uint64_t)(FIRST ? (id[q].x & 0x7fffffffu) : id[q].x));
+                    stage_fp<FQ>(slot, 6 * q + 3, src, 2 * (uint64_t)(FIRST ? (id[q].y & 0x7fffffffu) : id[q].y));
+                }
+            }
+            cp_async_commit();
+        };
+        fetch_ids(idc, 0);
+        issue(idc, 0);
+        if (ngroups > 1) fetch_ids(idn, 1);
+        for (uint64_t g = 0; g < ngroups; g++) {
+            uint2 cur[2] = {idc[0], idc[1]};
+            if (g + 1 < ngroups) {
+                issue(idn, (uint32_t)((g + 1) & 1));
+                idc[0] = idn[0]; idc[1] = idn[1];
+                if (g + 2 < ngroups) fetch_ids(idn, g + 2);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            const uint4* slot = ring + (g & 1) * stage_words;
+            const uint64_t j = j0 + 2 * g;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (j + q < j1) {
+                    stash[j + q] = cur[q];
+                    store_fp<FQ>(prefix, j + q, run);
+                    if (cur[q].y != NO_PARTNER) {
+                        const F xa = unstage_fp<FQ>(slot, 6 * q), xb = unstage_fp<FQ>(slot, 6 * q + 3);
+                        F d = xb - xa;
+                        const bool special = FIRST ? (xa.is_zero() || xb.is_zero() || d.is_zero())
+                                                   : (xa.v[FQ::N - 1] == 0xffffffffu || xb.v[FQ::N - 1] == 0xffffffffu || d.is_zero());
+                        if (special) d = pair_den_special<FQ, FIRST>(src, cur[q].x, cur[q].y);
+                        run = run * d;
+                    }
+                }
+            }
+        }
+    }
+
+    // 1 / (this thread's product) through a product tree over the CTA and one inversion
+    __syncthreads();                                     // every thread is done with its staging slots
+    store_fp<FQ>(sm, 128 + tid, run);
+    __syncthreads();
+    for (uint32_t s = 64; s >= 1; s >>= 1) {
+        if (tid < s) {
+            F a = load_fp<FQ>(sm, 2 * (s + tid)), c = load_fp<FQ>(sm, 2 * (s + tid) + 1);
+            store_fp<FQ>(sm, s + tid, a * c);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_fp<FQ>(sm, 1, load_fp<FQ>(sm, 1).inverse_binary());
+    __syncthreads();
+    for (uint32_t s = 1; s <= 64; s <<= 1) {
+        if (tid < s) {
+            F inv = load_fp<FQ>(sm, s + tid);
+            F a = load_fp<FQ>(sm, 2 * (s + tid)), c = load_fp<FQ>(sm, 2 * (s + tid) + 1);
+            store_fp<FQ>(sm, 2 * (s + tid), inv * c);
+            store_fp<FQ>(sm, 2 * (s + tid) + 1, inv * a);
+        }
+        __syncthreads();
+    }
+    F rinv = load_fp<FQ>(sm, 128 + tid);
+    __syncthreads();                                     // the tree is dead: the ring may be overwritten again
+
+    // pass 2 (backward): 1/d_j = rinv * prefix_j, then the affine addition; one output per stage
+    if (j0 < j1) {
+        auto issue2 = [&](const uint2 id, uint64_t j, uint32_t stage) {
+            uint4* slot = ring + stage * stage_words;
+            const uint64_t i1 = FIRST ? (id.x & 0x7fffffffu) : id.x;
+            stage_fp<FQ>(slot, 0, src, 2 * i1);
+            stage_fp<FQ>(slot, 3, src, 2 * i1 + 1);
+            if (id.y != NO_PARTNER) {
+                const uint64_t i2 = FIRST ? (id.y & 0x7fffffffu) : id.y;
+                stage_fp<FQ>(slot, 6, src, 2 * i2);
+                stage_fp<FQ>(slot, 9, src, 2 * i2 + 1);
+                stage_fp<FQ>(slot, 12, prefix, j);
+            }
+            cp_async_commit();
+        };
+        uint2 cur = stash[j1 - 1], nxt = make_uint2(0, NO_PARTNER);
+        issue2(cur, j1 - 1, 0);
+        if (j1 - 1 > j0) nxt = stash[j1 - 2];
+        uint32_t it = 0;
+        for (uint64_t j = j1; j-- > j0; it++) {
+            uint2 nn = make_uint2(0, NO_PARTNER);
+            if (j > j0) {
+                issue2(nxt, j - 1, (it + 1) & 1);
+                if (j > j0 + 1) nn = load_u2_early(stash + (j - 2));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            const uint4* slot = ring + (it & 1) * stage_words;
+            F x1 = unstage_fp<FQ>(slot, 0), y1 = unstage_fp<FQ>(slot, 3);
+            bool inf1 = pair_fix<FQ, FIRST>(cur.x, x1, y1);
+            if (cur.y != NO_PARTNER) {
+                F x2 = unstage_fp<FQ>(slot, 6), y2 = unstage_fp<FQ>(slot, 9);
+                const bool inf2 = pair_fix<FQ, FIRST>(cur.y, x2, y2);
+                if (inf1 || inf2) {
+                    if (inf1) { x1 = x2; y1 = y2; inf1 = inf2; }
+                } else if (x1 != x2) {
+                    const F dinv = rinv * unstage_fp<FQ>(slot, 12);
+                    rinv = rinv * (x2 - x1);
+                    const F lam = (y2 - y1) * dinv;
+                    const F x3 = lam.sqr() - x1 - x2;
+                    y1 = lam * (x1 - x3) - y1;
+                    x1 = x3;
+                } else if (y1 == y2 && !y1.is_zero()) {
+                    const F dinv = rinv * unstage_fp<FQ>(slot, 12);
+                    rinv = rinv * (y1 + y1);
+                    const F xx = x1.sqr();
+                    const F lam = (xx + xx + xx) * dinv;
+                    const F x3 = lam.sqr() - x1 - x1;
+                    y1 = lam * (x1 - x3) - y1;
+                    x1 = x3;
+                } else {
+                    inf1 = true;
+                }
+            }
+            if (inf1) {
+                x1 = F::zero();
+                y1 = F::zero();
+                x1.v[FQ::N - 1] = 0xffffffffu;
+            }
+            store_fp<FQ>(dst, 2 * j, x1);
+            store_fp<FQ>(dst, 2 * j + 1, y1);
+            cur = nxt;
+            nxt = nn;
+        }
+    }
+}
+
 // copies[f*n + i] = 2^(step*f) * P_i as affine points, f = 0..F-1 (copy 0 is the input itself)
 template <class FQ>
 __global__ void __launch_bounds__(128) k_ck_precompute(void* bases, uint64_t n, uint32_t F, uint32_t step) {
@@ -951,15 +1167,23 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     for (uint32_t r = 0; r < levels; r++) U[r + 1] = U[r] / 2 + nbS;
 
     // chunk size for the accumulate pass: exactly one resident wave of threads
-    static int occupancy_known = 0, resident_blocks[2] = {2, 2};
+    static int occupancy_known = 0, resident_blocks[3] = {2, 2, 3};
     if (!occupancy_known) {
         occupancy_known = 1;
 #ifndef APB_EMU
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_accumulate<FQ, 2, 0>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[0] = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_pairs<FQ, 1, 2>, 128, 0) == cudaSuccess && nb > 0) resident_blocks[1] = nb;
+        cudaFuncSetAttribute(k_msm_pairs2<Fq381, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES);
+        cudaFuncSetAttribute(k_msm_pairs2<Fq381, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES);
+        cudaFuncSetAttribute(k_msm_pairs2<Fq377, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES);
+        cudaFuncSetAttribute(k_msm_pairs2<Fq377, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_msm_pairs2<FQ, 1, 3>, 128, PAIR_SMEM_BYTES) == cudaSuccess && nb > 0) resident_blocks[2] = nb;
 #endif
     }
+    // pair-level kernel: 2 = cp.async staging through shared memory (default), 1 = register software pipeline
+    int pairs_variant = 2;
+    if (const char* e = getenv("APB_MSM_PAIRS")) pairs_variant = atoi(e) == 1 ? 1 : 2;
     uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[0] * 128;
     const uint64_t Macc = U[levels];
     uint32_t E = (uint32_t)((Macc + target_threads - 1) / target_threads);
@@ -1054,6 +1278,8 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     auto k_acc_lvl = k_msm_accumulate<FQ, 2, 1>;
     auto k_pairs_first = k_msm_pairs<FQ, 1, 2>;
     auto k_pairs_next = k_msm_pairs<FQ, 0, 2>;
+    auto k_pairs2_first = k_msm_pairs2<FQ, 1, 3>;
+    auto k_pairs2_next = k_msm_pairs2<FQ, 0, 3>;
     bool unbalanced = false;
     std::vector<uint32_t> bound(slices + 1);
     if (slices > 1) {
@@ -1096,14 +1322,21 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
                 int rc2 = u32_scan(cnt + (size_t)r * lvl_stride, off_r, nbS, ck->scan_tmp, off_r + nbS);
                 if (rc2 != APB_OK) return rc2;
             }
-            const uint64_t pair_threads = (uint64_t)g_num_sms * resident_blocks[1] * 128;
+            const uint64_t pair_threads = (uint64_t)g_num_sms * resident_blocks[pairs_variant] * 128;
             for (uint32_t r = 0; r < levels; r++) {
                 uint32_t Ep = (uint32_t)((Ue[r + 1] + pair_threads - 1) / pair_threads);
                 if (Ep < 4) Ep = 4;
                 const unsigned blocks = (unsigned)(((Ue[r + 1] + Ep - 1) / Ep + 127) / 128);
                 const uint32_t* off_in = r == 0 ? offsets0 : off + (size_t)(r - 1) * lvl_stride;
                 const uint32_t* off_out = off + (size_t)r * lvl_stride;
-                if (r == 0)
+                if (pairs_variant == 2) {
+                    if (r == 0)
+                        APB_KLAUNCH(k_pairs2_first, blocks, 128, PAIR_SMEM_BYTES, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in,
+                                    off_out, nbS, Ep, ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
+                    else
+                        APB_KLAUNCH(k_pairs2_next, blocks, 128, PAIR_SMEM_BYTES, (const uint32_t*)nullptr, (const void*)ck->lvl_pts[(r - 1) & 1],
+                                    off_in, off_out, nbS, Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, ck->lvl_stash);
+                } else if (r == 0)
                     APB_KLAUNCH(k_pairs_first, blocks, 128, 0, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in, off_out, nbS, Ep,
                                 ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
                 else
