@@ -50,14 +50,11 @@ def test_msm_bls12_377_and_batch(emu_lib):
         pc.check_msm_progression(emu_lib, 0, 48, k=3)
 
 
-@pytest.mark.parametrize("pairs", [2, 1])
-def test_msm_batched_affine_pair_levels(emu_lib, pairs):
+def test_msm_batched_affine_pair_levels(emu_lib):
     """the batched-affine pair levels in front of the accumulate (narrow digits make buckets long enough
     for 3 levels at these sizes): random, edge scalars, equal points / P + (-P) / infinity bases inside
-    a pair (doubling and cancellation branches), BLS12-377, batched commit, odd chunk sizes; both pair
-    kernels (2 = cp.async staging, the default; 1 = register pipeline)"""
-    with pc.env(APB_MSM_PAIRS=pairs):
-        _pair_level_cases(emu_lib)
+    a pair (doubling and cancellation branches), BLS12-377, batched commit, odd chunk sizes"""
+    _pair_level_cases(emu_lib)
 
 
 def _pair_level_cases(emu_lib):

@@ -59,14 +59,11 @@ def test_msm_duplicate_points_and_cancellation(gpu_lib):
     pc.check_msm_duplicates(gpu_lib, 1)
 
 
-@pytest.mark.parametrize("pairs", [2, 1])
 @pytest.mark.parametrize("curve", [0, 1])
-def test_msm_batched_affine_pair_levels(gpu_lib, curve, pairs):
+def test_msm_batched_affine_pair_levels(gpu_lib, curve):
     """the pair levels (default from 6 M bucket entries; forced here) on both curves: closed-form KAT with a
-    ragged 3-polynomial batch, edge scalars, and equal points / P + (-P) / infinity inside a pair; both pair
-    kernels (2 = cp.async staging, the default; 1 = register pipeline)"""
-    with pc.env(APB_MSM_PAIRS=pairs):
-        _pair_level_cases(gpu_lib, curve)
+    ragged 3-polynomial batch, edge scalars, and equal points / P + (-P) / infinity inside a pair"""
+    _pair_level_cases(gpu_lib, curve)
 
 
 def _pair_level_cases(gpu_lib, curve):

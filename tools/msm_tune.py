@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Sweeps the MSM's stage variants on one GPU: pair kernel (APB_MSM_PAIRS 1 = register pipeline, 2 = cp.async
-staging) x number of batched-affine levels x batch size, for 2^18-point commits (the prover's shape) and
+"""Sweeps the MSM's stage variants on one GPU: number of batched-affine levels x batch size (optionally
+APB_MSM_STEP / other environment knobs set by the caller), for 2^18-point commits (the prover's shape) and
 single MSMs of 2^18 / 2^20 / 2^22.  Prints per-phase CUDA-event times; every result is checked against the
 first variant of its shape.  Output: gpurun_out/msm_tune.json"""
 import json, os, sys, time
@@ -18,7 +18,7 @@ out = []
 shapes = [(18, 1), (18, 2), (18, 4), (18, 8), (18, 16), (20, 1), (22, 1)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
-variants = [(1, 0)] + [(p, l) for p in (1, 2) for l in (1, 2, 3, 4, 5)]
+variants = [(1, l) for l in (0, 1, 2, 3, 4, 5)]
 keys = {}
 for log_n, k in shapes:
     n = 1 << log_n
