@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libapb.so")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_acc.cu", "msm_pairs.cu", "msm_setup.cu", "poly.cu", "transcript.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_acc.cu", "msm_pairs_coop.cu", "msm_setup.cu", "poly.cu", "transcript.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",

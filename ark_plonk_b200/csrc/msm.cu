@@ -97,9 +97,17 @@ static int ck_alloc(int curve, size_t n, apb_ck_s** out) {
     ck->magic = CK_MAGIC;
     ck->curve = curve;
     ck->n = n;
-    size_t big = (size_t)1 << 24;
-    if (const char* e = getenv("APB_MSM_FULL_PRECOMP_MAX")) big = (size_t)atoll(e);
-    if (n <= big) { ck->step = 16; ck->F = 16; } else { ck->step = 64; ck->F = 4; }
+    // Digit width of the resident table (copy f holds 2^(step f) P_i).  16-bit digits (16 copies, 2^15 buckets) up to
+    // 2^21 points; from 2^22 points 20-bit digits (13 copies, 2^19 buckets): 13 instead of 16 additions per point, and the
+    // larger bucket reduction (1.45 ms instead of 0.36 ms on B200) is repaid from ~2^21.5 points (2^22: 183 -> 200 Mpts/s,
+    // profiles/r02_msm_step20.json).  Keys whose 13-copy table would not fit the HBM budget fall back to 4 copies with
+    // 64-bit steps (4 bucket windows of 16-bit digits).
+    size_t wide_min = (size_t)1 << 22, table_budget = (size_t)112 << 30;
+    if (const char* e = getenv("APB_MSM_WIDE_DIGITS_MIN")) wide_min = (size_t)atoll(e);
+    if (const char* e = getenv("APB_MSM_TABLE_BUDGET")) table_budget = (size_t)atoll(e);
+    if (n < wide_min && n * 16 * 96 <= table_budget) { ck->step = 16; ck->F = 16; }
+    else if (n * 13 * 96 <= table_budget && (uint64_t)n * 13 < ((uint64_t)1 << 31)) { ck->step = 20; ck->F = 13; }
+    else { ck->step = 64; ck->F = 4; }
     if (const char* e = getenv("APB_MSM_STEP")) {
         ck->step = (uint32_t)atoi(e);
         ck->F = (256 + ck->step - 1) / ck->step;
@@ -325,11 +333,11 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
     for (uint32_t r = 0; r < levels; r++) U[r + 1] = U[r] / 2 + nbS;
 
     // chunk size for the accumulate pass: exactly one resident wave of threads
-    static int resident_blocks[2][2] = {{0, 0}, {0, 0}};          // [curve][accumulate, pairs]
+    static int resident_blocks[2][2] = {{0, 0}, {0, 0}};          // [curve][accumulate, pair level]
     const int cv = ck->curve == APB_CURVE_BLS12_381 ? 0 : 1;
     if (!resident_blocks[cv][0]) {
         resident_blocks[cv][0] = msm_resident_blocks_accumulate(ck->curve);
-        resident_blocks[cv][1] = msm_resident_blocks_pairs(ck->curve);
+        resident_blocks[cv][1] = msm_resident_blocks_pairs_coop(ck->curve);
     }
     uint64_t target_threads = (uint64_t)g_num_sms * resident_blocks[cv][0] * 128;
     const uint64_t Macc = U[levels];
@@ -367,7 +375,7 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
         if ((rc = grow(&ck->lvl_words, &ck->lvl_words_cap, (size_t)levels * 2 * lvl_stride * 4)) != APB_OK) return rc;
         if ((rc = grow(&ck->lvl_pts[0], &ck->lvl_pts_cap[0], (size_t)U[1] * 96)) != APB_OK) return rc;
         if (levels > 1 && (rc = grow(&ck->lvl_pts[1], &ck->lvl_pts_cap[1], (size_t)U[2] * 96)) != APB_OK) return rc;
-        if ((rc = grow(&ck->lvl_prefix, &ck->lvl_prefix_cap, (size_t)U[1] * 48)) != APB_OK) return rc;
+        if ((rc = grow(&ck->lvl_prefix, &ck->lvl_prefix_cap, (size_t)(U[1] + 32) * 48)) != APB_OK) return rc;
         if ((rc = grow(&ck->lvl_stash, &ck->lvl_stash_cap, (size_t)U[1] * 8)) != APB_OK) return rc;
     }
     uint32_t a_bits, b_bits;
@@ -468,12 +476,9 @@ static int run_msm(apb_ck_s* ck, const MsmBatch& B, const void* d_scalars, int m
                 const unsigned blocks = (unsigned)(((Ue[r + 1] + Ep - 1) / Ep + 127) / 128);
                 const uint32_t* off_in = r == 0 ? offsets0 : off + (size_t)(r - 1) * lvl_stride;
                 const uint32_t* off_out = off + (size_t)r * lvl_stride;
-                if (r == 0)
-                    msm_launch_pairs(ck->curve, 1, blocks, (const uint32_t*)ck->entries, (const void*)ck->bases, off_in, off_out, nbS, Ep,
-                                     ck->lvl_pts[0], ck->lvl_prefix, ck->lvl_stash);
-                else
-                    msm_launch_pairs(ck->curve, 0, blocks, (const uint32_t*)nullptr, (const void*)ck->lvl_pts[(r - 1) & 1], off_in, off_out,
-                                     nbS, Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, ck->lvl_stash);
+                msm_launch_pairs_coop(ck->curve, r == 0, blocks, r == 0 ? (const uint32_t*)ck->entries : (const uint32_t*)nullptr,
+                                          r == 0 ? (const void*)ck->bases : (const void*)ck->lvl_pts[(r - 1) & 1], off_in, off_out, nbS, Ue[r + 1],
+                                          Ep, ck->lvl_pts[r & 1], ck->lvl_prefix, (Ue[r + 1] + 31) / 32 * 32, ck->lvl_stash);
             }
             acc_offsets = off + (size_t)(levels - 1) * lvl_stride;          // slice-relative from here on
         }

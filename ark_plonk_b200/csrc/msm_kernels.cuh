@@ -1,5 +1,5 @@
 // Shared declarations of the MSM translation units (msm.cu: host logic; msm_acc.cu: sort / accumulate / reduce
-// kernels; msm_pairs.cu: batched-affine pair levels; msm_setup.cu: key precomputation).  The kernels are split
+// kernels; msm_pairs_coop.cu: batched-affine pair levels; msm_setup.cu: key precomputation).  The kernels are split
 // over several files only so that nvcc compiles them in parallel; each file exports plain launcher functions.
 #pragma once
 #include "common.cuh"
@@ -65,11 +65,12 @@ void msm_launch_stitch(int curve, unsigned blocks, const uint32_t* offsets, uint
                        const void* partials, const int32_t* part_bucket);
 void msm_launch_tree(int curve, const void* in, void* out, const TreeJob* jobs, uint32_t njobs);
 int msm_resident_blocks_accumulate(int curve);
-// msm_pairs.cu
+// msm_pairs_coop.cu: `ids` = 8 bytes per output, `prefix` = 3 planes of `pstride` 16-byte chunks
 void msm_launch_level_counts(const uint32_t* offsets0, uint32_t nbuckets, uint32_t levels, uint32_t* cnt);
-void msm_launch_pairs(int curve, int first, unsigned blocks, const uint32_t* entries, const void* src, const uint32_t* off_in,
-                      const uint32_t* off_out, uint32_t nbuckets, uint32_t E, void* dst, void* prefix, uint2* stash);
-int msm_resident_blocks_pairs(int curve);
+void msm_launch_pairs_coop(int curve, int first, unsigned blocks, const uint32_t* entries, const void* src, const uint32_t* off_in,
+                           const uint32_t* off_out, uint32_t nbuckets, uint64_t max_out, uint32_t E, void* dst, void* prefix,
+                           uint64_t pstride, uint2* ids);
+int msm_resident_blocks_pairs_coop(int curve);
 // msm_setup.cu
 void msm_launch_ck_precompute(int curve, void* bases, uint64_t n, uint32_t F, uint32_t step);
 void msm_launch_srs_powers(int curve, void* bases, void* d_powers, uint64_t n, const void* d_pow2, const void* d_gen);

@@ -15,7 +15,7 @@ ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "ark_plonk_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libapb_emu.so")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_acc.cu", "msm_pairs.cu", "msm_setup.cu", "poly.cu", "transcript.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_acc.cu", "msm_pairs_coop.cu", "msm_setup.cu", "poly.cu", "transcript.cu"]
 FLAGS = ["-std=c++20", "-O2", "-DAPB_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC, "-w"]
 
 

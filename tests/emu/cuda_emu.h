@@ -43,7 +43,7 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 namespace apb_emu {
 inline thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 inline std::barrier<>* g_barrier = nullptr;
-inline std::barrier<>* g_warp_barriers = nullptr;   // unused for now
+inline thread_local std::barrier<>* t_warp_barrier = nullptr;      // of this thread's warp (apb_emu::warp_sync)
 inline uint8_t* g_dyn_smem = nullptr;
 inline uint32_t g_shfl_buf[2048][16];
 
@@ -54,7 +54,10 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
     g_barrier = &bar;
     std::vector<uint8_t> dyn(smem + 64);
     g_dyn_smem = dyn.data();
+    std::vector<std::unique_ptr<std::barrier<>>> warp_bars;        // warps = 32 consecutive linear thread ids
+    for (unsigned w = 0; w * 32 < nt; w++) warp_bars.emplace_back(new std::barrier<>(nt - w * 32 < 32 ? nt - w * 32 : 32));
     auto worker = [&](unsigned tid) {
+        t_warp_barrier = warp_bars[tid / 32].get();
         t_blockDim = block;
         t_gridDim = grid;
         t_threadIdx = dim3(tid % block.x, (tid / block.x) % block.y, tid / (block.x * block.y));
@@ -77,6 +80,9 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
     g_barrier = nullptr;
     g_dyn_smem = nullptr;
 }
+// a REAL barrier over the 32 lanes of the calling thread's warp: for kernels whose lanes exchange data through
+// shared memory (every lane of the warp must call it the same number of times)
+inline void warp_sync() { t_warp_barrier->arrive_and_wait(); }
 }  // namespace apb_emu
 
 #define threadIdx (apb_emu::t_threadIdx)

@@ -18,7 +18,9 @@ out = []
 shapes = [(18, 1), (18, 2), (18, 4), (18, 8), (18, 16), (20, 1), (22, 1)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
-variants = [(1, l) for l in (0, 1, 2, 3, 4, 5)]
+variants = [(2, l) for l in (0, 1, 2, 3, 4, 5, 6)]
+if os.environ.get("APB_TUNE_VARIANTS"):          # e.g. "2:3,2:4,1:3" = pairs kernel : levels
+    variants = [tuple(int(x) for x in v.split(":")) for v in os.environ["APB_TUNE_VARIANTS"].split(",")]
 keys = {}
 for log_n, k in shapes:
     n = 1 << log_n
@@ -33,7 +35,7 @@ for log_n, k in shapes:
     ln = (C.c_size_t * k)(*([n] * k))
     ref = None
     for pairs, levels in variants:
-        env = {"APB_MSM_PAIRS": str(pairs), "APB_MSM_AFFINE_LEVELS": str(levels), "APB_MSM_AFFINE_MIN": "0"}
+        env = {"APB_MSM_AFFINE_LEVELS": str(levels), "APB_MSM_AFFINE_MIN": "0"}
         os.environ.update(env)
         res = np.zeros((k, 18), dtype=np.uint64)
         ms, ph = [], []
