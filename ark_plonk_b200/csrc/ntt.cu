@@ -46,6 +46,11 @@ struct NttPassArgs {
     const void* post_hi;
     int post_const;           // ... or the constant 1/N (ifft)
     uint32_t size_inv[8];
+    // k_ntt_pass8: the tile's log_t butterfly stages grouped into rounds of up to three.  In a round every thread holds
+    // the 8 elements whose flat tile index (d * C + c) differs in bits [lb, lb + 3); bit ob of `mask` set = own bit ob
+    // is a butterfly stage of this round (high to low).
+    uint32_t nrounds;
+    uint32_t round_lb[8], round_mask[8];
 };
 
 template <class FR>
@@ -141,6 +146,133 @@ __global__ void __launch_bounds__(512) k_ntt_pass(NttPassArgs A) {
             F s;
 #pragma unroll
             for (int i = 0; i < 8; i++) s.v[i] = A.size_inv[i];
+            v = v * s;
+        }
+        store_fp<FR>(out, oidx, v);
+    }
+}
+
+// ---- register-resident pass: R = 4 elements per thread, two stages between shared-memory exchanges ----------------------
+// The radix-2 kernel above (kept for tiles of fewer than 4 elements) does one stage per shared-memory round trip and CTA
+// barrier.  Here a thread keeps R elements in registers and runs log2(R) stages on them before the tile is exchanged
+// through shared memory once (one barrier per ROUND, not per stage); the first round reads global memory straight into
+// registers and the last one writes straight from them.  Shared-memory positions are XOR-swizzled (the three 3-bit
+// fields above bit 3 folded into the low three bits), so the 8 lanes of every LDS.128 / STS.128 phase hit 8 different
+// 16-byte bank groups whatever stride the round uses - data planes and the tile's root table alike.  In the LAST round of
+// a tile (own bits = the lowest tile bits) the twiddles depend only on the register index: w_4 is loaded once and three
+// of the four butterflies need no product.
+APB_D uint32_t ntt_swz(uint32_t i) { return i ^ ((i >> 3) & 7u) ^ ((i >> 6) & 7u) ^ ((i >> 9) & 7u); }
+
+template <class FR>
+APB_D void ntt_bfly(Fp<FR>& u, Fp<FR>& v) {          // (u, v) <- (u + v, u - v)
+    const Fp<FR> t = u - v;
+    u = u + v;
+    v = t;
+}
+
+template <class FR, int LR>
+__global__ void __launch_bounds__(256) k_ntt_pass_reg(NttPassArgs A) {
+    constexpr int R = 1 << LR;                       // elements per thread
+    typedef Fp<FR> F;
+    APB_DYN_SMEM(smem);
+    const uint32_t T = 1u << A.log_t, C = 1u << A.log_c, TC = T << A.log_c;
+    uint4* xlo = reinterpret_cast<uint4*>(smem);
+    uint4* xhi = xlo + TC;
+    uint4* wlo = xhi + TC;
+    uint4* whi = wlo + (T >> 1);
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;             // nth == TC / R
+    const uint64_t tile = blockIdx.x;
+    const uint64_t ta = tile % A.na, tb = tile / A.na;
+    const uint64_t base_in = ta * A.in_a + tb * A.in_b;
+    const uint64_t base_out = ta * A.out_a + tb * A.out_b;
+    const uint4* in = reinterpret_cast<const uint4*>(A.in) + 2 * A.in_batch_stride * blockIdx.y;
+    uint4* out = reinterpret_cast<uint4*>(A.out) + 2 * A.out_batch_stride * blockIdx.y;
+
+    // roots of the tile transform: w_T^j = w_N^(j * N/T)
+    for (uint32_t j = tid; j < (T >> 1); j += nth) {
+        F w = load_fp<FR>(A.roots, (uint64_t)j << (A.log_n - A.log_t));
+        smem_put<FR>(wlo, whi, ntt_swz(j), w);
+    }
+    F e[R];
+    uint32_t lb = A.round_lb[0], mask = A.round_mask[0];
+    uint32_t i0 = ((tid >> lb) << (lb + LR)) | (tid & ((1u << lb) - 1));
+    // first round: global -> registers (zero-extension and coset pre-scale fused)
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        const uint32_t i = i0 + ((uint32_t)k << lb), c = i & (C - 1), d = i >> A.log_c;
+        const uint64_t idx = base_in + d * A.in_sd + c * A.in_sc;
+        if (idx < A.in_len) {
+            e[k] = load_fp<FR>(in, idx);
+            if (A.pre_lo) {
+                F s = load_fp<FR>(A.pre_lo, idx & ((1u << COSET_LO_BITS) - 1)) * load_fp<FR>(A.pre_hi, idx >> COSET_LO_BITS);
+                e[k] = e[k] * s;
+            }
+        } else {
+            e[k] = F::zero();
+        }
+    }
+    __syncthreads();                                 // root table complete
+    for (uint32_t r = 0;; r++) {
+        // butterflies of this round, own bits high to low
+        if (lb == A.log_c) {
+            // bottom-aligned window (always all LR stages, halves R/2 .. 1): twiddle index = (k mod half) * T / (2 half),
+            // the same in every thread
+            static_assert(LR == 2, "constant twiddles of the last round are written out for 4 elements per thread");
+            const F w2 = smem_get<FR>(wlo, whi, ntt_swz(T >> 2));
+            ntt_bfly<FR>(e[0], e[2]);
+            ntt_bfly<FR>(e[1], e[3]); e[3] = e[3] * w2;
+            ntt_bfly<FR>(e[0], e[1]);
+            ntt_bfly<FR>(e[2], e[3]);
+        } else {
+#pragma unroll
+            for (int ob = LR - 1; ob >= 0; ob--) {
+                if (!((mask >> ob) & 1u)) continue;
+                const uint32_t lh = lb + ob - A.log_c;                   // stage half = 2^lh (in tile indices)
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    if (k & (1 << ob)) continue;
+                    ntt_bfly<FR>(e[k], e[k | (1 << ob)]);
+                    if (lh > 0) {
+                        const uint32_t j = ((i0 + ((uint32_t)k << lb)) >> A.log_c) & ((1u << lh) - 1);
+                        e[k | (1 << ob)] = e[k | (1 << ob)] * smem_get<FR>(wlo, whi, ntt_swz(j << (A.log_t - 1 - lh)));
+                    }
+                }
+            }
+        }
+        if (r + 1 == A.nrounds) break;
+        // exchange: every thread writes its 8 positions, then picks up the 8 positions of the next window
+#pragma unroll
+        for (int k = 0; k < R; k++) smem_put<FR>(xlo, xhi, ntt_swz(i0 + ((uint32_t)k << lb)), e[k]);
+        __syncthreads();
+        lb = A.round_lb[r + 1];
+        mask = A.round_mask[r + 1];
+        i0 = ((tid >> lb) << (lb + LR)) | (tid & ((1u << lb) - 1));
+#pragma unroll
+        for (int k = 0; k < R; k++) e[k] = smem_get<FR>(xlo, xhi, ntt_swz(i0 + ((uint32_t)k << lb)));
+    }
+
+    // registers -> global: position d of the in-place transform holds output bitrev(d) (inter-pass twiddle / final scaling fused)
+    const uint64_t half_n = (uint64_t)1 << (A.log_n - 1);
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        const uint32_t i = i0 + ((uint32_t)k << lb), c = i & (C - 1), d = i >> A.log_c;
+        const uint32_t ko = A.log_t ? (__brev(d) >> (32 - A.log_t)) : 0;
+        F v = e[k];
+        const uint64_t oidx = base_out + ko * A.out_sk + c * A.out_sc;
+        if (A.tw_mult) {
+            const uint64_t ex = (ta * C + c) * ko * A.tw_mult;
+            if (ex != 0) {
+                F w = (ex < half_n) ? load_fp<FR>(A.roots, ex) : load_fp<FR>(A.roots, ex - half_n).neg();
+                v = v * w;
+            }
+        }
+        if (A.post_lo) {
+            F s = load_fp<FR>(A.post_lo, oidx & ((1u << COSET_LO_BITS) - 1)) * load_fp<FR>(A.post_hi, oidx >> COSET_LO_BITS);
+            v = v * s;
+        } else if (A.post_const) {
+            F s;
+#pragma unroll
+            for (int q = 0; q < 8; q++) s.v[q] = A.size_inv[q];
             v = v * s;
         }
         store_fp<FR>(out, oidx, v);
@@ -244,9 +376,9 @@ static int build_tables(apb_domain_s* d) {
 }
 
 static void plan_passes(apb_domain_s* d) {
-    // measured on B200 (tools/ntt_tune.py, profiles/r01_ntt_tune.txt): three passes of <= 2^8-point tiles
-    // beat two passes of 2^10-point tiles by ~10 % (fewer barrier-separated stages per tile, more CTAs/SM)
-    int maxbits = 8;
+    // tiles of up to 2^10 points: two passes up to 2^20 (every extra pass costs one more twiddle product per element
+    // and one more trip through L2 / HBM); the register-resident pass kernel exchanges a tile once per three stages
+    int maxbits = 10;
     if (const char* e = getenv("APB_NTT_MAX_LOG_TILE")) maxbits = atoi(e);
     if (maxbits < 1) maxbits = 1;
     if (maxbits > 10) maxbits = 10;
@@ -311,7 +443,7 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
     const bool inverse = kind == APB_NTT_IFFT || kind == APB_NTT_COSET_IFFT;
     const uint32_t L = d->log_n;
     const int P = d->npass;
-    int log_cols_max = 1;
+    int log_cols_max = 2;
     if (const char* e = getenv("APB_NTT_LOG_COLS")) log_cols_max = atoi(e);
     if (P > 1 && d->scratch_elems < d->n * batch) {
         cudaFree(d->scratch);
@@ -375,17 +507,42 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
         if (last && kind == APB_NTT_IFFT) { A.post_const = 1; memcpy(A.size_inv, d->size_inv, 32); }
         const uint64_t tiles = d->n >> (lt + A.log_c);
         const uint32_t tc = 1u << (lt + A.log_c);
-        uint32_t threads = tc / 2;
-        if (threads < 32) threads = 32;
-        if (threads > 512) threads = 512;
         const size_t smem = (size_t)tc * 32 + (size_t)(1u << lt) * 16 + 64;
         static size_t smem_set = 0;
         if (smem > 48 * 1024 && smem > smem_set) {
             APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<Fr381>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<Fr377>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass_reg<Fr381, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            APB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass_reg<Fr377, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             smem_set = 200 * 1024;
         }
-        APB_KLAUNCH(k_ntt_pass<FR>, dim3((unsigned)tiles, (unsigned)batch), threads, smem, A);
+        // 4 elements per thread, two stages per round (profiles/r02_ntt_tune.txt: 8 elements per thread at 134 registers
+        // were 25 % SLOWER than the radix-2 kernel, 4 elements at 72 registers are 8-9 % faster); APB_NTT_LOG_RADIX=0
+        // selects the radix-2 kernel (also used for tiles of fewer than 4 elements)
+        int lr = 2;
+        if (const char* e = getenv("APB_NTT_LOG_RADIX")) lr = atoi(e) == 0 ? 0 : 2;
+        if (lr == 2 && tc >= 4 && (tc >> 2) <= 256 && lt >= 2) {
+            // rounds of up to `lr` stages; the first round takes the remainder so that the last window is bottom-aligned
+            uint32_t hi = lt + A.log_c, remaining = lt, take = lt % lr ? lt % lr : lr;
+            A.nrounds = 0;
+            while (remaining) {
+                const uint32_t lb = hi - lr;
+                uint32_t mask = 0;
+                for (uint32_t b = hi - take; b < hi; b++) mask |= 1u << (b - lb);
+                A.round_lb[A.nrounds] = lb;
+                A.round_mask[A.nrounds] = mask;
+                A.nrounds++;
+                hi -= take;
+                remaining -= take;
+                take = lr;
+            }
+            APB_KLAUNCH((k_ntt_pass_reg<FR, 2>), dim3((unsigned)tiles, (unsigned)batch), tc >> 2, smem, A);
+        } else {
+            uint32_t threads = tc / 2;
+            if (threads < 32) threads = 32;
+            if (threads > 512) threads = 512;
+            APB_KLAUNCH(k_ntt_pass<FR>, dim3((unsigned)tiles, (unsigned)batch), threads, smem, A);
+        }
         mbits += lt;
     }
     APB_CHECK_LAUNCH();

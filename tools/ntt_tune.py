@@ -25,8 +25,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         d.close()
     print(json.dumps(res))
 else:
-    for mt in (10, 9, 8, 7):
-        for lc in (0, 1, 2, 3, 4):
-            env = dict(os.environ, APB_NTT_MAX_LOG_TILE=str(mt), APB_NTT_LOG_COLS=str(lc))
-            out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-            print("max_tile", mt, "log_cols", lc, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
+    # APB_NTT_LOG_RADIX: 2 / 3 = register-resident pass with 4 / 8 elements per thread, 0 = radix-2 stages in shared memory
+    for lr in (2, 3, 0):
+        for mt in ((10, 9, 8) if lr else (10, 8, 7)):
+            for lc in (0, 1, 2):
+                env = dict(os.environ, APB_NTT_LOG_RADIX=str(lr), APB_NTT_MAX_LOG_TILE=str(mt), APB_NTT_LOG_COLS=str(lc))
+                out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
+                print("log_radix", lr, "max_tile", mt, "log_cols", lc, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
