@@ -84,6 +84,7 @@ class Lib:
         c.apb_plonk_lookup_z2.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         c.apb_plonk_quotient.argtypes = [ci, vpp, vp, vp, vp, sz]
         c.apb_plonk_quotient_full.argtypes = [ci, vpp, vp, vp, vp, sz]
+        c.apb_plonk_quotient_range.argtypes = [ci, vpp, vp, vp, vp, sz, sz, sz]
         c.apb_poly_eval.argtypes = [ci, sz, vpp, szp, vp, vp]
         c.apb_poly_divide_linear.argtypes = [ci, vp, sz, vp, vp]
         c.apb_transcript_new.argtypes = [C.c_char_p, sz, vpp]

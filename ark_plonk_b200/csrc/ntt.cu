@@ -28,6 +28,21 @@ extern int g_num_sms;
 extern int g_profile;
 double g_ntt_ms_total = 0.0;              // device time of transforms while profiling (apb_set_profiling)
 unsigned long long g_ntt_count = 0;
+struct NttPending { cudaEvent_t a, b; unsigned long long batch; };
+static std::vector<NttPending> g_ntt_pending;        // recorded, not yet read (see apb_ntt_batch_dev)
+static std::mutex g_ntt_pending_mu;
+static void ntt_resolve_pending() {                  // caller holds g_ntt_pending_mu
+    for (NttPending& p : g_ntt_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_ntt_ms_total += ms;
+            g_ntt_count += p.batch;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_ntt_pending.clear();
+}
 static const int COSET_LO_BITS = 10;
 
 struct NttPassArgs {
@@ -557,19 +572,18 @@ extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, siz
     if (in_len > d->n) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: in_len %zu > domain size %zu", in_len, d->n);
     if (batch == 0) return APB_OK;
     if (!d_out || (!d_in && in_len)) return set_err(APB_ERR_INVALID_ARG, "apb_ntt: null buffer");
+    // profiling (apb_set_profiling): the two events are only RECORDED here and read when the totals are asked for -
+    // a cudaEventSynchronize per transform would put a host round trip behind every NTT of a proof
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    struct Ev2 { cudaEvent_t *a, *b; ~Ev2() { if (*a) cudaEventDestroy(*a); if (*b) cudaEventDestroy(*b); } } pev{&pe0, &pe1};
     if (g_profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cur_stream()); }
     int rc = d->curve == APB_CURVE_BLS12_381
                  ? run_ntt<Fr381>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch)
                  : run_ntt<Fr377>(d, kind, d_in, in_len, in_stride, d_out, out_stride, batch);
-    if (g_profile) {
+    if (pe0) {
         cudaEventRecord(pe1, cur_stream());
-        cudaEventSynchronize(pe1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, pe0, pe1);
-        g_ntt_ms_total += ms;
-        g_ntt_count += batch;
+        std::lock_guard<std::mutex> lk(g_ntt_pending_mu);
+        g_ntt_pending.push_back(NttPending{pe0, pe1, (unsigned long long)batch});
+        if (g_ntt_pending.size() > 8192) ntt_resolve_pending();
     }
     if (rc != APB_OK) return rc;
     if (sync) APB_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
@@ -577,6 +591,10 @@ extern "C" int apb_ntt_batch_dev(apb_domain_t d, int kind, const void* d_in, siz
 }
 
 extern "C" void apb_ntt_totals(double* ms, unsigned long long* transforms, int reset) {
+    {
+        std::lock_guard<std::mutex> lk(g_ntt_pending_mu);
+        ntt_resolve_pending();
+    }
     if (ms) *ms = g_ntt_ms_total;
     if (transforms) *transforms = g_ntt_count;
     if (reset) { g_ntt_ms_total = 0.0; g_ntt_count = 0; }

@@ -400,10 +400,11 @@ APB_D Fp<FR> gate_curve_add(const Fp<FR>& sep, const Fp<FR>& x1, const Fp<FR>& y
     return (xy_consistency + x3_consistency + y3_consistency) * sep;
 }
 template <class FR>
-__global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, void* out, uint64_t n4) {
+__global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, void* out, uint64_t n4, uint64_t first, uint64_t count) {
     typedef Fp<FR> F;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
+    if (i >= count) return;
+    i += first;                                      // this call evaluates points [first, first + count) of the 4n coset
     const uint64_t j = i + 4 >= n4 ? i + 4 - n4 : i + 4;
     const F alpha = arg_fp<FR>(A.alpha.v), beta = arg_fp<FR>(A.beta.v), gamma = arg_fp<FR>(A.gamma.v);
     const F a = load_fp<FR>(A.wl, i), b = load_fp<FR>(A.wr, i), c = load_fp<FR>(A.wo, i), d = load_fp<FR>(A.w4, i);
@@ -753,7 +754,16 @@ extern "C" int apb_plonk_combine_split(int curve, const void* d_t, const void* d
 // lookup_sep K1 K2 K3 | range_sep logic_sep fixed_sep var_sep coeff_a coeff_d), 4 inverse vanishing values
 extern "C" int apb_plonk_quotient_full(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
                                        void* d_out, size_t n4) {
+    return apb_plonk_quotient_range(curve, ptrs29, scalars16, vh_inv4, d_out, n4, 0, n4);
+}
+
+// points [first, first + count) only (all vectors are still the full 4n-point ones: "next row" values wrap around):
+// one proof split over several GPUs evaluates a slice per rank
+extern "C" int apb_plonk_quotient_range(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
+                                        void* d_out, size_t n4, size_t first, size_t count) {
     APB_API_LOCK();
+    if (first > n4 || count > n4 - first) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: range outside the domain");
+    if (count == 0) return APB_OK;
     if (bad_curve(curve)) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: bad curve");
     if (!ptrs29 || !scalars16 || !vh_inv4 || !d_out) return set_err(APB_ERR_INVALID_ARG, "apb_plonk_quotient: null argument");
     APB_REQUIRE_INIT();
@@ -766,8 +776,8 @@ extern "C" int apb_plonk_quotient_full(int curve, const void* const* ptrs29, con
     Fr4* sc = &A.alpha;
     for (int i = 0; i < 16; i++) sc[i] = mk4(scalars16 + 4 * i);
     for (int i = 0; i < 4; i++) A.vh_inv[i] = mk4(vh_inv4 + 4 * i);
-    DISPATCH_FR(curve, APB_KLAUNCH(k_quotient<Fr381>, nblk(n4, 128), 128, 0, A, d_out, (uint64_t)n4),
-                APB_KLAUNCH(k_quotient<Fr377>, nblk(n4, 128), 128, 0, A, d_out, (uint64_t)n4));
+    DISPATCH_FR(curve, APB_KLAUNCH(k_quotient<Fr381>, nblk(count, 128), 128, 0, A, d_out, (uint64_t)n4, (uint64_t)first, (uint64_t)count),
+                APB_KLAUNCH(k_quotient<Fr377>, nblk(count, 128), 128, 0, A, d_out, (uint64_t)n4, (uint64_t)first, (uint64_t)count));
     APB_CHECK_LAUNCH();
     return APB_OK;
 }

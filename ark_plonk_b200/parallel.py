@@ -6,7 +6,9 @@
   single all-gather; every rank folds the G partials on the host (G-1 group additions).
   NCCL has no elliptic-curve reduction, so reduction = gather + local adds.
 * `DistributedCommitter`: one proof over N GPUs, SPMD - every rank runs the prover, the MSM work of
-  every commit batch is split evenly, only 144-byte partial sums are exchanged.
+  every commit batch is split evenly, only 144-byte partial sums are exchanged; the independent 4n coset FFTs of
+  the quotient round are spread by polynomial and the quotient evaluation by index range, both re-assembled with
+  an in-place NVLink all-gather (`all_gather_inplace`).
 * A single NTT does not shard (replicas only).
 """
 from __future__ import annotations
@@ -104,6 +106,24 @@ class DistributedCommitter:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.results = torch.zeros((k_max + max(self.world, 1)) * 18, dtype=torch.int64, device=device)
         self.batches = 0
+        # collectives on arena slices are enqueued behind the kernels of the library's stream (no host synchronisation)
+        self.lib_stream = torch.cuda.ExternalStream(self.lib.c.apb_stream()) if str(device).startswith("cuda") else None
+        self.gathers = 0
+
+    def all_gather_inplace(self, arena, off: int, chunk_elems: int):
+        """The `world` chunks of `chunk_elems` Fr elements at arena offset `off`: chunk r is valid on rank r when this
+        is called; on return (stream order) every rank holds all of them.  Used by the prover to spread independent
+        transforms / index ranges over the ranks: NVLink all-gather of evaluation vectors."""
+        if self.world == 1:
+            return
+        whole = arena.view(off, self.world * chunk_elems)
+        mine = arena.view(off + self.rank * chunk_elems, chunk_elems)
+        if self.lib_stream is not None:
+            with torch.cuda.stream(self.lib_stream):
+                dist.all_gather_into_tensor(whole, mine, group=self.group)
+        else:
+            dist.all_gather_into_tensor(whole, mine, group=self.group)
+        self.gathers += 1
 
     def commit(self, arena, offs, lens) -> np.ndarray:
         """called by EVERY rank with its own copy of the k polynomials at arena element offsets `offs`:

@@ -483,8 +483,17 @@ class Prover:
             srcs.append(pi_poly)
             ev_names.append("pi")
         ev = A.alloc(len(srcs) * N4)
+        # one proof over several GPUs: the coset FFTs are independent, so rank r transforms polynomials
+        # [r * per, (r + 1) * per) and the evaluation vectors are all-gathered in place over NVLink; the
+        # K mod world left-over polynomials are transformed by every rank
+        com = self.committer
+        split = com is not None and com.world > 1 and A.tensor is not None and N4 % com.world == 0
+        per = len(srcs) // com.world if split else 0
         for k, s in enumerate(srcs):                                         # 10 coset FFTs on 4n (quotient_poly.rs:74-120)
-            self._ntt(dom4, NTT_COSET_FFT, A, s, n, ev + k * N4)
+            if k >= per * (com.world if split else 0) or k // per == com.rank:
+                self._ntt(dom4, NTT_COSET_FFT, A, s, n, ev + k * N4)
+        if per:
+            com.all_gather_inplace(A, ev, per * N4)
         E = {nm: ev + k * N4 for k, nm in enumerate(ev_names)}
         q_ev = A.alloc(N4)
         order = [E["wl"], E["wr"], E["wo"], E["w4"], E["z"], E["z2"], E["f"], E["table"], E["h1"], E["h2"], E.get("pi"),
@@ -494,7 +503,13 @@ class Prover:
         ptrs = (C.c_void_p * 29)(*[A.ptr(o) if o is not None else None for o in order])
         scal = _mont_list(curve, [alpha, beta, gamma, delta, epsilon, zeta, lookup_sep, K1, K2, K3,
                                   range_sep, logic_sep, fixed_sep, var_sep, gates.EMBEDDED_A[curve], gates.EMBEDDED_D[curve]])
-        lib.check(lib.c.apb_plonk_quotient_full(curve, ptrs, scal.ctypes.data, pk.vh_inv.ctypes.data, A.ptr(q_ev), N4))
+        if split:                                                            # every rank evaluates its slice of the coset
+            chunk = N4 // com.world
+            lib.check(lib.c.apb_plonk_quotient_range(curve, ptrs, scal.ctypes.data, pk.vh_inv.ctypes.data, A.ptr(q_ev), N4,
+                                                     com.rank * chunk, chunk))
+            com.all_gather_inplace(A, q_ev, chunk)
+        else:
+            lib.check(lib.c.apb_plonk_quotient_full(curve, ptrs, scal.ctypes.data, pk.vh_inv.ctypes.data, A.ptr(q_ev), N4))
         # the evaluation vectors are dead: t_poly reuses their space (the stream is in order, so
         # the coset_ifft reads q_ev before anything enqueued later can overwrite it)
         A.release(mark4)

@@ -34,8 +34,17 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: keep NCCL's version / debug banner on stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its version
+# banner to fd 1 from C, past sys.stdout) and the result line goes to a private duplicate of the original stdout
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -261,7 +270,7 @@ def run_reference(args):
     if args.workload == "prove":
         log_n = args.log_n or 18
         line = reference_prove(args, log_n, cores)
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     if args.workload == "msm":
         log_n = args.log_n or 18
@@ -295,7 +304,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "arkworks-0.3-algorithm restatement in C (oracle/c); the Rust reference cannot be built here",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -358,7 +367,8 @@ def run_b200(args):
         if split and world > 1:
             from ark_plonk_b200 import parallel
             committer = parallel.DistributedCommitter(0, ck, device="cuda")
-        pr = gp.Prover(0, ck, committer=committer)
+        # (a torch-backed arena at N > 1: the round-4 coset FFTs / quotient slices are all-gathered on arena views)
+        pr = gp.Prover(0, ck, committer=committer, arena_device="cuda" if committer is not None else None)
         pk = pr.preprocess(circ, commit_verifier_key=False)
         wires = gp.wires_to_mont(circ)
         wires_pinned = torch.from_numpy(wires.view(np.int64)).pin_memory()
@@ -662,7 +672,7 @@ def run_b200(args):
                  "dtype": "u32-limb integers (381/255-bit Montgomery)", "data": "synthetic", "gpu_launches": int(launches),
                  "clocks": clocks})
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

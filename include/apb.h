@@ -160,6 +160,10 @@ int apb_plonk_quotient(int curve, const void* const* ptrs25, const uint64_t* sca
  * fixed-base / variable-base separation challenges + the embedded curve's COEFF_A, COEFF_D */
 int apb_plonk_quotient_full(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
                             void* d_out, size_t n4);
+/* the same for the points [first, first + count) of the 4n coset only (inputs are the full vectors; d_out is the full
+ * output vector, only that slice is written): lets the ranks of a multi-GPU proof evaluate one slice each */
+int apb_plonk_quotient_range(int curve, const void* const* ptrs29, const uint64_t* scalars16, const uint64_t* vh_inv4,
+                             void* d_out, size_t n4, size_t first, size_t count);
 /* k evaluations polys[j](points[j]) -> out_vals (host, Montgomery); DensePolynomial::evaluate */
 int apb_poly_eval(int curve, size_t k, const void* const* d_polys, const size_t* lens, const uint64_t* points,
                   uint64_t* out_vals);

@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
             circ = bc.build(0, degree, [int(b, 16) for b in case["blinders"]])
             ck = kzg.CommitterKey.from_tau(0, int(case["tau"], 16), circ.n + 1, lib=lib)
             com = parallel.DistributedCommitter(0, ck, device="cuda", lib=lib)
-            pr = gp.Prover(0, ck, lib=lib, committer=com)
+            pr = gp.Prover(0, ck, lib=lib, committer=com, arena_device="cuda")
             pk = pr.preprocess(circ, commit_verifier_key=False)
             for _ in range(2):
                 blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")

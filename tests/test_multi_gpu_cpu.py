@@ -85,10 +85,12 @@ def _prove_worker(rank, world, port, emu_path, result_q):
     ck = kzg.CommitterKey.from_tau(0, tau, circ.n + 1, lib=lib)
     com = parallel.DistributedCommitter(0, ck, group=None, device="cpu", lib=lib)
     # SPMD: every rank runs the whole prover; each commit batch is split evenly, 144-byte partials all-reduced
-    pr = gp.Prover(0, ck, lib=lib, committer=com)
+    # (a torch-backed arena: the coset FFTs / quotient slices of round 4 are exchanged with all-gathers on arena views)
+    pr = gp.Prover(0, ck, lib=lib, committer=com, arena_device="cpu")
     pk = pr.preprocess(circ, commit_verifier_key=False)
     blob = pr.prove(pk, gp.wires_to_mont(circ), b"ark")
     ok = hashlib.sha256(blob).hexdigest() == case["proof_sha256"] and com.batches == 5   # 5 batched commit calls per proof
+    ok = ok and com.gathers == 2                     # coset-FFT vectors + quotient slices
     result_q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
