@@ -177,6 +177,8 @@ class Prover:
         self.msm_calls += k
         if self.committer is not None and self.committer.world > 1:
             out = self.committer.commit(arena, offs, lens)
+            if self.phase_log is not None:       # this rank's share of the batch
+                self.phase_log.append((k, self.lib.last_device_ms(), self.lib.msm_phase_ms()))
             return [(out[i], self.lib.g1_compress(self.curve, out[i])) for i in range(k)]
         so = (C.c_size_t * k)(*offs)
         bo = (C.c_size_t * k)(*([0] * k))

@@ -449,7 +449,9 @@ def run_b200(args):
             "config": {"workload": "BLS12-381 KZG10 prove, BenchCircuit 2^%d gates (with lookups), %d real rows" % (log_n, circ.rows),
                        "curve": "BLS12-381", "msm_per_proof": 29, "ntt_n_per_proof": 17, "ntt_4n_per_proof": 11,
                        "multi_gpu": ("one proof, SPMD over %d ranks: every rank runs the prover, the points of each of the %d commit "
-                                     "batches are split evenly, one all-reduce of 144-byte partial sums per batch" % (world, ncalls))
+                                     "batches are split evenly (one all-reduce of 144-byte partial sums per batch), the 10 coset FFTs "
+                                     "of round 4 are spread by polynomial and the quotient by index range (NVLink all-gathers); "
+                                     "phase_split = rank 0's share" % (world, ncalls))
                                     if split and world > 1 else ("%d independent proofs" % world if world > 1 else "single GPU"),
                        "proof_sha256": sha, "golden_match": golden_match,
                        "extra_ms_without_discarded_commitments": no_dead_ms,
@@ -457,7 +459,7 @@ def run_b200(args):
                        "l2": "inputs exceed L2 (resident key table %d MB, prover key %d MB)" % ((n + 1) * 16 * 96 >> 20, pk.arena.elems * 32 >> 20),
                        "vs_baseline_note": "this value / published 20184 ms (Ryzen 7 3700X CPU, reference README.md:107); < 1 is faster"},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": len(proof) + 29 * 3024},
-            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels) + k_msm_accumulate (XYZZ)",
+            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs_coop (batched-affine levels) + k_msm_accumulate (XYZZ)",
                          "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
                          "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12),
                          "frac_whole_msm": pts_total * MSM_IMAD_PER_POINT / (msm_calls_ms * 1e-3) / wide_peak if msm_calls_ms else None,
@@ -591,7 +593,7 @@ def run_b200(args):
                        "l2": "inputs exceed L2 (resident base table %d MB)" % (n * 16 * 96 >> 20)},
             "e2e": {"value": total_n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32,
                     "d2h_bytes_per_step": 144 + 15 * 192},
-            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs (batched-affine levels) + k_msm_accumulate (XYZZ)",
+            "roofline": {"kernel": "bucket accumulation stage of the MSM: k_msm_pairs_coop (batched-affine levels) + k_msm_accumulate (XYZZ)",
                          "bound": "int32", "achieved": achieved, "peak": wide_peak / 1e12,
                          "unit": "T wide-IMAD/s", "frac": achieved / (wide_peak / 1e12),
                          "frac_whole_msm": n * K * MSM_IMAD_PER_POINT / (msm_calls_ms * 1e-3) / wide_peak if msm_calls_ms else None,
