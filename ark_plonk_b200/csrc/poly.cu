@@ -317,6 +317,7 @@ struct QuotientArgs {
     Fr4 alpha, beta, gamma, delta, epsilon, zeta, lookup_sep, k1, k2, k3;
     Fr4 range_sep, logic_sep, fixed_sep, var_sep, coeff_a, coeff_d;   // embedded curve: a x^2 + y^2 = 1 + d x^2 y^2
     Fr4 vh_inv[4];
+    Fr4 alpha_sq, lsep_sq, lsep_cu, eps_opd;                  // alpha^2, lookup_sep^2, lookup_sep^3, epsilon (1 + delta): host-computed
 };
 
 // f (f-1) (f-2) (f-3)   (widget/range.rs:64-73, widget/logic.rs:100-108)
@@ -441,14 +442,14 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, void* out, uin
         F copy = (a + beta * load_fp<FR>(A.s1, i) + gamma) * (b + beta * load_fp<FR>(A.s2, i) + gamma);
         copy = copy * (c + beta * load_fp<FR>(A.s3, i) + gamma) * (d + beta * load_fp<FR>(A.s4, i) + gamma);
         copy = copy * zn * alpha;
-        perm = ident - copy + (zi - F::one()) * (l1 * alpha.sqr());
+        perm = ident - copy + (zi - F::one()) * (l1 * arg_fp<FR>(A.alpha_sq.v));
     }
     // lookup
     F look;
     {
         const F delta = arg_fp<FR>(A.delta.v), eps = arg_fp<FR>(A.epsilon.v), zeta = arg_fp<FR>(A.zeta.v);
-        const F ls = arg_fp<FR>(A.lookup_sep.v), lsq = ls.sqr(), lcu = lsq * ls;
-        const F opd = delta + F::one(), eopd = eps * opd;
+        const F ls = arg_fp<FR>(A.lookup_sep.v), lsq = arg_fp<FR>(A.lsep_sq.v), lcu = arg_fp<FR>(A.lsep_cu.v);
+        const F opd = delta + F::one(), eopd = arg_fp<FR>(A.eps_opd.v);
         const F fi = load_fp<FR>(A.f, i), ti = load_fp<FR>(A.table, i), tn = load_fp<FR>(A.table, j);
         const F h1i = load_fp<FR>(A.h1, i), h1n = load_fp<FR>(A.h1, j), h2i = load_fp<FR>(A.h2, i);
         const F z2i = load_fp<FR>(A.z2, i), z2n = load_fp<FR>(A.z2, j);
@@ -776,6 +777,15 @@ extern "C" int apb_plonk_quotient_range(int curve, const void* const* ptrs29, co
     Fr4* sc = &A.alpha;
     for (int i = 0; i < 16; i++) sc[i] = mk4(scalars16 + 4 * i);
     for (int i = 0; i < 4; i++) A.vh_inv[i] = mk4(vh_inv4 + 4 * i);
+    {   // challenge powers every point needs: once on the host instead of once per thread
+        host::Field f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fr381>() : host::Field::make<Fr377>();
+        uint64_t opd[4];
+        f.sqr(A.alpha_sq.v, A.alpha.v);
+        f.sqr(A.lsep_sq.v, A.lookup_sep.v);
+        f.mul(A.lsep_cu.v, A.lsep_sq.v, A.lookup_sep.v);
+        f.add(opd, A.delta.v, f.one);
+        f.mul(A.eps_opd.v, A.epsilon.v, opd);
+    }
     DISPATCH_FR(curve, APB_KLAUNCH(k_quotient<Fr381>, nblk(count, 128), 128, 0, A, d_out, (uint64_t)n4, (uint64_t)first, (uint64_t)count),
                 APB_KLAUNCH(k_quotient<Fr377>, nblk(count, 128), 128, 0, A, d_out, (uint64_t)n4, (uint64_t)first, (uint64_t)count));
     APB_CHECK_LAUNCH();
