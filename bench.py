@@ -247,8 +247,10 @@ def reference_prove(args, log_n, cores):
         "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": value / 20184.0 if log_n == 18 else None,
         "dtype": "u64-limb integers", "data": "synthetic",
-        "config": {"workload": "BLS12-381 KZG10 prove, BenchCircuit 2^%d gates (with lookups)" % log_n, "curve": "BLS12-381",
-                   "msm_per_proof": 29, "ntt_n_per_proof": 17, "ntt_4n_per_proof": 14},
+        "config": {"workload": "BLS12-381 KZG10 prove, BenchCircuit 2^%d gates (with lookups), %d real rows" % (log_n, (1 << (log_n - 1)) + 2),
+                   "curve": "BLS12-381", "msm_per_proof": 29, "ntt_n_per_proof": 17, "ntt_4n_per_proof": 14,
+                   "ntt_4n_note": "the reference's schedule: 13 coset FFTs + 1 coset IFFT; the B200 arm executes 11 of them per proof "
+                                  "(the 3 coset FFTs of key polynomials are resident with the prover key)"},
         "cpu_baseline": {"value": value, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "arkworks-0.3-algorithm restatement in C (oracle/c); the Rust reference cannot be built here. "
@@ -657,7 +659,7 @@ def run_b200(args):
                        "l2": "vector %d MB %s L2" % (n * 32 >> 20, "exceeds" if n * 32 > 126 << 20 else "fits in")},
             "e2e": {"value": world * 2 * n * 32 / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n * 32,
                     "d2h_bytes_per_step": n * 32},
-            "roofline": {"kernel": "k_ntt_pass", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_ntt_pass_reg (4 elements per thread, two stages per shared-memory exchange)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                          "int32": {"achieved": imad, "peak": wide_peak / 1e12, "unit": "T wide-IMAD/s", "frac": imad / (wide_peak / 1e12)},
                          "note": "2*N*32 algorithmic bytes; the transform is INT32-issue bound (SURVEY 8d), both fractions reported"},
