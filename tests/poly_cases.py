@@ -172,3 +172,26 @@ def check_grand_products(lib, curve, log_n, seed=3):
     finally:
         arena.close()
         dom.close()
+
+
+def check_quotient_range(lib, curve, n4=64, seed=11):
+    """apb_plonk_quotient_range over ragged slices == apb_plonk_quotient_full over the whole 4n coset (the multi-GPU
+    proof evaluates one slice per rank): random input vectors, all custom gate selectors present, public inputs;
+    also the argument checks of the range entry point"""
+    p = FR[curve].p
+    rnd = random.Random(seed)
+    arena = Arena(lib, 32 * n4 + 64)
+    try:
+        offs = [_up(arena, [rnd.randrange(p) for _ in range(n4)], curve) for _ in range(29)]
+        ptrs = (C.c_void_p * 29)(*[arena.ptr(o) for o in offs])
+        scal = np.ascontiguousarray(enc.fr_to_mont(curve, [rnd.randrange(p) for _ in range(16)]))
+        vh = np.ascontiguousarray(enc.fr_to_mont(curve, [rnd.randrange(1, p) for _ in range(4)]))
+        full, parts = arena.alloc(n4), arena.alloc(n4)
+        lib.check(lib.c.apb_plonk_quotient_full(curve, ptrs, scal.ctypes.data, vh.ctypes.data, arena.ptr(full), n4))
+        cuts = [0, 1, n4 // 3, n4 // 3, n4 - 5, n4]                 # incl. an empty slice and the wrap-around rows
+        for lo, hi in zip(cuts, cuts[1:]):
+            lib.check(lib.c.apb_plonk_quotient_range(curve, ptrs, scal.ctypes.data, vh.ctypes.data, arena.ptr(parts), n4, lo, hi - lo))
+        assert np.array_equal(arena.download(full, n4), arena.download(parts, n4))
+        assert lib.c.apb_plonk_quotient_range(curve, ptrs, scal.ctypes.data, vh.ctypes.data, arena.ptr(parts), n4, n4 - 2, 3) != 0
+    finally:
+        arena.close()

@@ -25,3 +25,8 @@ def test_kzg_open_and_domain_helpers(emu_lib):
     with pc.env(APB_MSM_C=8, APB_NTT_MAX_LOG_TILE=4):
         pc.check_kzg_open_and_domain_helpers(emu_lib, 0, 5)
         pc.check_kzg_open_and_domain_helpers(emu_lib, 1, 4, seed=13)
+
+
+def test_quotient_range_matches_full(emu_lib):
+    poly_cases.check_quotient_range(emu_lib, 0)
+    poly_cases.check_quotient_range(emu_lib, 1, n4=32, seed=12)

@@ -164,6 +164,11 @@ def test_poly_grand_products(gpu_lib):
     poly_cases.check_grand_products(gpu_lib, 1, 10, seed=11)
 
 
+def test_poly_quotient_range_matches_full(gpu_lib):
+    poly_cases.check_quotient_range(gpu_lib, 0, n4=1 << 14)
+    poly_cases.check_quotient_range(gpu_lib, 1, n4=1 << 10, seed=12)
+
+
 def test_kzg_open_and_domain_helpers(gpu_lib):
     pc.check_kzg_open_and_domain_helpers(gpu_lib, 0, 10)
     pc.check_kzg_open_and_domain_helpers(gpu_lib, 1, 8, seed=14)
