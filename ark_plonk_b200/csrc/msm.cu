@@ -9,11 +9,12 @@
 // Design (B200-first, see DESIGN.md "MSM"):
 //   * The commitment key is resident in HBM together with F-1 precomputed multiples
 //     2^(step*f) * P_i (affine).  A signed c-bit digit at position w = f*G + g of scalar i is
-//     then "add +-copy_f[i] to bucket |d|-1 of effective window g": with step = 16, c = 16,
-//     G = 1 all 16 digit positions share ONE bucket set and no window doublings remain.
+//     then "add +-copy_f[i] to bucket |d|-1 of effective window g": with step = c = 16 (up to 2^21
+//     points; step = c = 20 from 2^22 points) and G = 1 all digit positions share ONE bucket set and
+//     no window doublings remain.
 //   * digits -> histogram -> exclusive scan -> scatter gives the (bucket, point) pairs sorted
 //     by bucket (a counting sort; keys are bucket ids).
-//   * large lists first go through batched-affine PAIR LEVELS (k_msm_pairs): the points of every
+//   * large lists first go through batched-affine PAIR LEVELS (k_msm_pairs_coop): the points of every
 //     bucket are added pairwise as affine points with all denominators of a CTA inverted together
 //     (5M+1S per addition instead of 8M+2S), two or three times, which halves the list each time.
 //   * accumulation walks the (remaining) sorted list in equal chunks per thread (perfect balance

@@ -61,9 +61,9 @@ struct NttPassArgs {
     const void* post_hi;
     int post_const;           // ... or the constant 1/N (ifft)
     uint32_t size_inv[8];
-    // k_ntt_pass8: the tile's log_t butterfly stages grouped into rounds of up to three.  In a round every thread holds
-    // the 8 elements whose flat tile index (d * C + c) differs in bits [lb, lb + 3); bit ob of `mask` set = own bit ob
-    // is a butterfly stage of this round (high to low).
+    // k_ntt_pass_reg: the tile's log_t butterfly stages grouped into rounds of up to LR.  In a round every thread holds
+    // the 2^LR elements whose flat tile index (d * C + c) differs in bits [lb, lb + LR); bit ob of `mask` set = own bit
+    // ob is a butterfly stage of this round (high to low).
     uint32_t nrounds;
     uint32_t round_lb[8], round_mask[8];
 };
