@@ -55,6 +55,7 @@ class Lib:
         c.apb_msm_batch_dev.argtypes = [vp, sz, vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), ci, vp]
         c.apb_g1_compress.argtypes = [ci, vp, vp]
         c.apb_g1_add.argtypes = [ci, vp, vp, vp]
+        c.apb_g1_fold.argtypes = [ci, sz, vp, vp, sz, vp]
         c.apb_msm_totals.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), ci]
         c.apb_msm_totals.restype = None
         c.apb_ntt_totals.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), ci]
@@ -171,6 +172,14 @@ class Lib:
         b = np.ascontiguousarray(b, dtype=np.uint64)
         out = np.zeros(18, dtype=np.uint64)
         self.check(self.c.apb_g1_add(curve, self._ptr(a), self._ptr(b), self._ptr(out)))
+        return out
+
+    def g1_fold(self, curve: int, pieces: np.ndarray, group, k: int) -> np.ndarray:
+        """out[j] = sum of pieces[p] with group[p] == j: (npieces, 18) normalised points -> (k, 18), one inversion"""
+        pieces = np.ascontiguousarray(pieces, dtype=np.uint64).reshape(-1, 18)
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        out = np.zeros((k, 18), dtype=np.uint64)
+        self.check(self.c.apb_g1_fold(curve, pieces.shape[0], self._ptr(pieces), grp.ctypes.data, k, self._ptr(out)))
         return out
 
     def imad_peak(self):

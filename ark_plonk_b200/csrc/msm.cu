@@ -728,6 +728,52 @@ extern "C" int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_
     memcpy(out_xyz + 12, f.one, 48);
     return APB_OK;
 }
+// Folds per-GPU partial sums: out[j] = sum of the pieces p with group[p] == j (normalised Jacobian in, normalised out),
+// all k results normalised with ONE field inversion.  The N-GPU commit split hands every rank (k + N - 1) pieces per batch.
+extern "C" int apb_g1_fold(int curve, size_t npieces, const uint64_t* pieces_xyz, const uint32_t* group, size_t k, uint64_t* out_xyz) {
+    if ((npieces && (!pieces_xyz || !group)) || (k && !out_xyz)) return set_err(APB_ERR_INVALID_ARG, "apb_g1_fold: null argument");
+    if (curve != APB_CURVE_BLS12_381 && curve != APB_CURVE_BLS12_377) return set_err(APB_ERR_INVALID_ARG, "apb_g1_fold: bad curve");
+    host::Group grp;
+    grp.f = curve == APB_CURVE_BLS12_381 ? host::Field::make<Fq381>() : host::Field::make<Fq377>();
+    const host::Field& f = grp.f;
+    std::vector<host::Pt> tot(k);
+    for (size_t j = 0; j < k; j++) grp.set_identity(tot[j]);
+    for (size_t p = 0; p < npieces; p++) {
+        if (group[p] >= k) return set_err(APB_ERR_INVALID_ARG, "apb_g1_fold: group index out of range");
+        const uint64_t* j = pieces_xyz + 18 * p;
+        if (f.is_zero(j + 12)) continue;                     // identity
+        host::Pt a;
+        memcpy(a.x, j, 48);
+        memcpy(a.y, j + 6, 48);
+        f.sqr(a.zz, j + 12);
+        f.mul(a.zzz, a.zz, j + 12);
+        grp.add(tot[group[p]], tot[group[p]], a);
+    }
+    std::vector<uint64_t> prod(6 * k), prefix(6 * k);
+    uint64_t run[6], inv[6];
+    f.set(run, f.one);
+    for (size_t j = 0; j < k; j++) {
+        f.set(&prefix[6 * j], run);
+        if (grp.is_identity(tot[j])) continue;
+        f.mul(&prod[6 * j], tot[j].zz, tot[j].zzz);
+        f.mul(run, run, &prod[6 * j]);
+    }
+    f.inv(inv, run);
+    for (size_t jj = k; jj-- > 0;) {
+        uint64_t* o = out_xyz + 18 * jj;
+        memset(o, 0, 18 * 8);
+        if (grp.is_identity(tot[jj])) continue;
+        uint64_t pinv[6], zi2[6], zi3[6];
+        f.mul(pinv, inv, &prefix[6 * jj]);               // 1 / (zz * zzz)
+        f.mul(inv, inv, &prod[6 * jj]);
+        f.mul(zi2, pinv, tot[jj].zzz);                   // 1 / zz
+        f.mul(zi3, pinv, tot[jj].zz);                    // 1 / zzz
+        f.mul(o, tot[jj].x, zi2);
+        f.mul(o + 6, tot[jj].y, zi3);
+        memcpy(o + 12, f.one, 48);
+    }
+    return APB_OK;
+}
 extern "C" void apb_msm_phase_ms(double out[4]) {
     for (int i = 0; i < 4; i++) out[i] = g_phase_ms[i];
 }

@@ -13,6 +13,8 @@
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -109,6 +111,12 @@ class DistributedCommitter:
         # collectives on arena slices are enqueued behind the kernels of the library's stream (no host synchronisation)
         self.lib_stream = torch.cuda.ExternalStream(self.lib.c.apb_stream()) if str(device).startswith("cuda") else None
         self.gathers = 0
+        # host staging of the partial sums (pinned on a GPU group): one copy in, one copy out per batch
+        self.h_stage = torch.zeros_like(self.results, device="cpu")
+        if self.lib_stream is not None:
+            self.h_stage = self.h_stage.pin_memory()
+        self.exchange_ms = 0.0         # wall time of the partial-sum exchanges (includes waiting for the slowest rank)
+        self.fold_ms = 0.0             # host folding of the pieces
 
     def all_gather_inplace(self, arena, off: int, chunk_elems: int):
         """The `world` chunks of `chunk_elems` Fr elements at arena offset `off`: chunk r is valid on rank r when this
@@ -135,8 +143,9 @@ class DistributedCommitter:
             kk = min(self.k_max, k - base)
             pieces = split_pieces(lens[base:base + kk], self.world)
             mine = [(i, p) for i, p in enumerate(pieces) if p[3] == self.rank]
-            res = self.results[: max(len(pieces), 1) * 18]
-            res.zero_()
+            nres = max(len(pieces), 1) * 18
+            res, h = self.results[:nres], self.h_stage[:nres]
+            h.zero_()
             if mine:
                 m = len(mine)
                 so = (C.c_size_t * m)(*[int(offs[base + j]) + lo for _, (j, lo, _, _) in mine])
@@ -144,18 +153,20 @@ class DistributedCommitter:
                 ln = (C.c_size_t * m)(*[hi - lo for _, (_, lo, hi, _) in mine])
                 part = np.zeros((m, 18), dtype=np.uint64)
                 self.lib.check(self.lib.c.apb_msm_batch_dev(self.ck._h, m, arena.base, so, bo, ln, 1, part.ctypes.data))
-                host = torch.from_numpy(part.view(np.int64))
-                for row, (slot, _) in enumerate(mine):
-                    res[slot * 18:(slot + 1) * 18].copy_(host[row])
+                first = mine[0][0]                      # a rank's pieces are consecutive slots
+                h[first * 18:(first + m) * 18] = torch.from_numpy(part.view(np.int64).reshape(-1))
+            t0 = time.perf_counter()
             if self.world > 1:
+                res.copy_(h, non_blocking=True)
                 dist.all_reduce(res, group=self.group)          # slots are disjoint: the sum is a gather
-            parts = res.cpu().numpy().view(np.uint64).reshape(-1, 18)
-            done = set()
-            for slot, (j, _, _, _) in enumerate(pieces):
-                if j in done:
-                    out[base + j] = self.lib.g1_add(self.curve, out[base + j], parts[slot])
-                else:
-                    out[base + j] = parts[slot]
-                    done.add(j)
+                h.copy_(res, non_blocking=True)
+                if self.lib_stream is not None:
+                    torch.cuda.current_stream().synchronize()
+            parts = h.numpy().view(np.uint64).reshape(-1, 18)
+            t1 = time.perf_counter()
+            if pieces:                                    # one C call: sums per polynomial, one shared inversion
+                out[base:base + kk] = self.lib.g1_fold(self.curve, parts[:len(pieces)], [j for j, _, _, _ in pieces], kk)
+            self.exchange_ms += (t1 - t0) * 1e3
+            self.fold_ms += (time.perf_counter() - t1) * 1e3
             self.batches += 1
         return out

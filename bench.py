@@ -414,17 +414,24 @@ def run_b200(args):
         # per-phase split of one profiled proof (outside the timed regions): MSM / NTT / other
         lib.ntt_totals(reset=True)
         pr.phase_log = []
+        if committer is not None:
+            committer.exchange_ms = committer.fold_ms = 0.0
         barrier()
         t0 = time.perf_counter()
         pr.prove(pk, None, b"ark", wires_resident=w_res)
         prof_ms = (time.perf_counter() - t0) * 1e3
         log, pr.phase_log = pr.phase_log, None
+        comm_split = None
+        if committer is not None:
+            comm_split = {"partial_sum_exchange_ms": committer.exchange_ms, "host_fold_ms": committer.fold_ms}
         msm_ms = sum(m for _, m, _ in log)
         ntt_ms, ntt_cnt = lib.ntt_totals()
         phase_split = {"msm_ms": msm_ms, "ntt_ms": ntt_ms, "other_ms": max(prof_ms - msm_ms - ntt_ms, 0.0), "profiled_proof_ms": prof_ms,
                        "msm_calls": len(log), "msm_count": sum(k for k, _, _ in log), "ntt_transforms": int(ntt_cnt),
                        "msm_accumulate_ms": sum(p["accumulate"] for _, _, p in log), "msm_sort_ms": sum(p["sort"] for _, _, p in log),
                        "msm_reduce_ms": sum(p["reduce"] for _, _, p in log)}
+        if comm_split:
+            phase_split.update(comm_split)
         # extra (not the headline): the same proof without the 14 commitments whose results the reference discards
         barrier()
         t0 = time.perf_counter()

@@ -103,6 +103,9 @@ int apb_msm_batch_dev(apb_ck_t ck, size_t k, const void* d_scalars, const size_t
 /* out = a + b for two points in the (X, Y, Z) form apb_msm returns; folds per-GPU partial sums of a
  * point-split MSM (host side, a handful of field operations) */
 int apb_g1_add(int curve, const uint64_t a_xyz[18], const uint64_t b_xyz[18], uint64_t out_xyz[18]);
+/* out[j] = sum of the pieces p with group[p] == j, j < k (npieces normalised Jacobian points in, k normalised points out, one
+ * shared field inversion): folds the per-GPU partial sums of a commit batch that was split over several GPUs */
+int apb_g1_fold(int curve, size_t npieces, const uint64_t* pieces_xyz, const uint32_t* group, size_t k, uint64_t* out_xyz);
 
 /* ark-serialize compressed G1Affine (48 bytes; flags in the top bits of the last byte):
  * what `Commitment` contributes to the transcript (plonk-core/src/transcript.rs:27-33). */
