@@ -249,3 +249,26 @@ def check_msm_pass_split(lib, curve=0, n=48, k=4, limit_split=4000, limit_fail=1
                 raise AssertionError("a pass above the 32-bit entry bound must be refused")
     finally:
         ck.close()
+
+
+def check_g1_fold(lib, curve, seed=3):
+    """apb_g1_fold (folding the per-GPU partial sums of a split commit batch): groups of 0, 1 and several pieces,
+    identity pieces, a group that cancels to the identity - against the oracle's group law"""
+    cv = CURVES[curve]
+    rnd = random.Random(seed)
+    pts = [cv.mul(cv.G, rnd.randrange(1, 1 << 64)) for _ in range(6)]
+    pts.append(cv.neg(pts[5]))                                                                    # cancels pts[5]
+    pts.append(None)                                                                              # identity piece
+    group = [0, 0, 0, 2, 2, 3, 3, 2]                                                              # group 1 stays empty
+    one = enc.fq_to_mont(curve, [1])[0]
+    xyz = np.zeros((len(pts), 18), dtype=np.uint64)
+    for i, P in enumerate(pts):
+        if P is not None:
+            xyz[i, :12] = enc.g1_affine_to_mont(curve, [P])[0]
+            xyz[i, 12:] = one
+    out = lib.g1_fold(curve, xyz, group, 4)
+    exp = [None] * 4
+    for P, g in zip(pts, group):
+        exp[g] = cv.add(exp[g], P)
+    assert [enc.g1_from_xyz(curve, o) for o in out] == exp
+    assert exp[1] is None and exp[3] is None

@@ -19,6 +19,11 @@ def test_ntt_single_and_multi_pass(emu_lib, log_n, in_len, max_tile, log_cols):
         pc.check_ntt(emu_lib, 0, log_n, in_len)
 
 
+def test_g1_fold(emu_lib):
+    pc.check_g1_fold(emu_lib, 0)
+    pc.check_g1_fold(emu_lib, 1, seed=4)
+
+
 def test_ntt_bls12_377(emu_lib):
     with pc.env(APB_NTT_MAX_LOG_TILE=3, APB_NTT_LOG_COLS=2):
         pc.check_ntt(emu_lib, 1, 6, 40)

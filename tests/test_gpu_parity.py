@@ -77,6 +77,11 @@ def _pair_level_cases(gpu_lib, curve):
         pc.check_msm_duplicates(gpu_lib, curve)
 
 
+def test_g1_fold(gpu_lib):
+    pc.check_g1_fold(gpu_lib, 0)
+    pc.check_g1_fold(gpu_lib, 1, seed=4)
+
+
 def test_msm_windowed_geometry(gpu_lib):
     with pc.env(APB_MSM_STEP=64):
         pc.check_msm_tau(gpu_lib, 0, 3000)
