@@ -177,7 +177,12 @@ struct Fp {
         O[N - 1] = addc(O[N - 1], 0);
     }
 
-    APB_HD friend Fp operator*(const Fp& a, const Fp& b) {
+    // REDUCE = false leaves the result in [0, 2p) (no final conditional subtraction): allowed wherever the value is
+    // only ever used as an OPERAND of further products - a CIOS product of operands a, b < 2p is again below
+    // a b / R + p < 2p (4p < R for every field here), and the one reduce_once of the product that finally consumes it
+    // makes the result canonical.  Never compare, add, subtract or store-as-output such a value.
+    template <bool REDUCE>
+    APB_HD static Fp mul_impl(const Fp& a, const Fp& b) {
         uint32_t X[N], Y[N];
         cios_step<true>(X, Y, a.v, b.v[0]);
         _Pragma("unroll") for (int i = 1; i < N; i += 2) {
@@ -190,9 +195,11 @@ struct Fp {
         r.v[0] = add_cc(X[0], Y[1]);
         _Pragma("unroll") for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
         r.v[N - 1] = addc(X[N - 1], 0);
-        reduce_once(r.v);
+        if (REDUCE) reduce_once(r.v);
         return r;
     }
+    APB_HD friend Fp operator*(const Fp& a, const Fp& b) { return mul_impl<true>(a, b); }
+    APB_HD Fp mul_lazy(const Fp& b) const { return mul_impl<false>(*this, b); }
     // ---- Montgomery square (base fields only: needs 3p < 2^(32N)) ---------------------------
     // CIOS where step i multiplies a_i by the vector [0,..,0, a_i, 2*a_{>i}]: every off-diagonal
     // product a_i*a_j is formed once (N(N+1)/2 = 78 instead of 144 for N = 12).  2*a_{>i} is read

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs_coop(const uint2* ids, 
                                            : (xa.v[FQ::N - 1] == 0xffffffffu || xb.v[FQ::N - 1] == 0xffffffffu || d.is_zero());
                 if (special) d = pair_den_special<FQ, FIRST>(src, own.x, own.y);
                 stage<FQ>(prefix + j, run, pstride);
-                run = run * d;
+                run = run.mul_lazy(d);               // only ever a product operand again (see Fp::mul_impl)
             }
             warp_barrier();                          // this stage may be overwritten by the fetch after next
             own = own_next;
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs_coop(const uint2* ids, 
         __syncthreads();
     }
     if (tid == 0) store_fp<FQ>(sm, 1, load_fp<FQ>(sm, 1).inverse_binary());   // one thread: latency matters, not throughput
+    // (the leaves may be in [0, 2p); every tree node is a full product of two of them, hence canonical)
     __syncthreads();
     for (uint32_t s = 1; s <= 64; s <<= 1) {
         if (tid < s) {
@@ -321,14 +322,14 @@ __global__ void __launch_bounds__(128, MINB) k_msm_pairs_coop(const uint2* ids, 
                     fast = !odd && (dx.v[0] | dx.v[FQ::N - 1]) != 0;
                 }
                 if (fast) {
-                    const F dinv = rinv * pre;
-                    rinv = rinv * dx;
+                    const F dinv = rinv.mul_lazy(pre);                   // dinv, rinv, lam: product operands only
+                    rinv = rinv.mul_lazy(dx);
                     F y1 = unstage<FQ>(r1 + 3), y2 = unstage<FQ>(r2 + 3);
                     if (FIRST) {
                         if (own.x >> 31) y1 = y1.neg();
                         if (own.y >> 31) y2 = y2.neg();
                     }
-                    const F lam = (y2 - y1) * dinv;
+                    const F lam = (y2 - y1).mul_lazy(dinv);
                     const F x3 = lam.sqr() - unstage<FQ>(r1) - unstage<FQ>(r2);
                     const F y3 = lam * (unstage<FQ>(r1) - x3) - y1;
                     stage<FQ>(st + lane * PC_RS, x3);    // this lane's own first-input slot: nobody else reads it
