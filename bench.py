@@ -11,8 +11,11 @@ One "step" = one pass of the hot path over one batch of synthetic input:
         key) + the pointwise kernels; the proof bytes are compared with the ORACLE's golden proof of the
         same instance (tests/golden/plonk_bench_2p*.json -> "golden_match"); metric = ms per proof.
         With --gpus N the default is ONE proof over N GPUs, SPMD (strong scaling): every rank runs the
-        prover, each commit batch's MSM work is split evenly, 144-byte partial sums are all-reduced;
-        --prove-mode replicas = N independent proofs (weak scaling).
+        prover, each commit batch's MSM work is split evenly (144-byte partial sums all-reduced, folded by
+        one C call), the 10 coset FFTs of round 4 are spread by polynomial and the quotient by index range
+        (in-place NVLink all-gathers of the evaluation vectors); `phase_split` then is rank 0's share and
+        carries the time spent waiting at the partial-sum exchanges; --prove-mode replicas = N independent
+        proofs (weak scaling).
   msm : one KZG10 commitment MSM over 2^L (default 2^18) BLS12-381 G1 points per GPU
         (resident powers + precomputed table in HBM, seeded uniform scalars); --total-log-n T fixes the
         TOTAL size at 2^T points split over the ranks instead (strong scaling)
