@@ -483,9 +483,10 @@ static int run_ntt(apb_domain_s* d, int kind, const void* d_in, size_t in_len, u
         A.out_batch_stride = last ? out_stride : d->n;
         A.roots = inverse ? d->itw : d->tw;
         A.in_len = first ? in_len : ~(uint64_t)0;
-        // columns: keep T*C <= 2048 elements (64 KB of shared memory -> >= 2 CTAs per SM) and
-        // enough tiles to fill the chip a few times over
-        uint32_t lc = 11 > lt ? 11 - lt : 0;
+        // columns: keep T*C <= 1024 elements (the register-resident pass kernel runs T*C/4 <= 256 threads per tile; 48 KB of
+        // shared memory -> 3-4 CTAs per SM) and enough tiles to fill the chip a few times over
+        uint32_t lc = 10 > lt ? 10 - lt : 0;
+        if (getenv("APB_NTT_LOG_RADIX") && atoi(getenv("APB_NTT_LOG_RADIX")) == 0) lc = 11 > lt ? 11 - lt : 0;   // radix-2 kernel: up to 2048
         if ((int)lc > log_cols_max) lc = log_cols_max;
         while (lc > 0 && ((d->n >> (lt + lc)) * batch) < (uint64_t)4 * g_num_sms) lc--;
         if (!last) {
